@@ -1,0 +1,94 @@
+"""ctypes binding of libctxnerf.so (include/ctxnerf.h).
+
+There is deliberately no fallback: if the library is missing or a call fails
+the wrapper raises.  The product path never routes through PyTorch eager math
+or the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libctxnerf.so")
+
+_lib = None
+
+P = c_void_p  # every device pointer
+
+
+_SIGNATURES = {
+    "ctx_abi_version": (c_int, []),
+    "ctx_error_string": (c_char_p, [c_int]),
+    "ctx_posenc_fwd": (c_int, [P, P, c_int64, c_int, c_int, c_int, c_int, P]),
+    "ctx_posenc_bwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_int, P]),
+    "ctx_raygen_fwd": (c_int, [c_int, c_int, c_float, c_float, c_float, c_float, P, c_int, P, c_int64,
+                               c_int, c_float, c_float, c_int, c_float, c_float, c_int, c_int, P,
+                               c_uint64, c_int, P, P, P, P, P, P, P]),
+    "ctx_stratified_fwd": (c_int, [P, c_int64, P, c_int64, c_int64, c_int, c_int, c_int, P, c_uint64, P, P]),
+    "ctx_ndc_fwd": (c_int, [c_int, c_int, c_float, c_float, P, P, c_int64, P, P, P]),
+    "ctx_ndc_bwd": (c_int, [c_int, c_int, c_float, c_float, P, P, P, P, c_int64, P, P, P]),
+    "ctx_composite_fwd": (c_int, [P, P, P, P, c_int64, c_int, c_int, P, P, P, P, P, P]),
+    "ctx_composite_bwd": (c_int, [P, P, P, P, c_int64, c_int, c_int, P, P, P, P, P, P, P]),
+    "ctx_resample_fwd": (c_int, [P, c_int64, c_int, P, c_int64, P, P, c_int, c_uint64, c_int64, c_int,
+                                 c_int, P, P, P, c_int64, c_int, P, P]),
+    "ctx_resample_bwd": (c_int, [P, c_int64, c_int, P, c_int64, P, c_int, c_uint64, c_int64, c_int, c_int,
+                                 P, P, P]),
+    "ctx_mlp_net_bytes": (c_int, []),
+    "ctx_mlp_describe": (c_int, [c_int, ctypes.c_uint32, c_int, c_int, c_int, P]),
+    "ctx_mlp_pack": (c_int, [P, P, c_int, P, P, P, P]),
+    "ctx_mlp_fwd": (c_int, [P, P, P, c_int, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int64, P, P, P]),
+    "ctx_tcgen05_selftest": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
+}
+
+
+class CtxNerfError(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    """Load libctxnerf.so (once).  Raises loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CtxNerfError(
+            f"{LIB_PATH} not found: build the CUDA extension first "
+            "(python __graft_entry__.py build, or python contexture-nerf_b200/ctxnerf/build.py). "
+            "ctxnerf has no CPU or eager-PyTorch fallback.")
+    handle = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        try:
+            fn = getattr(handle, name)
+        except AttributeError:
+            continue  # reported by tests/test_abi_symbols.py; calling it raises below
+        fn.restype = res
+        fn.argtypes = args
+    _lib = handle
+    return handle
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        msg = lib().ctx_error_string(int(code))
+        raise CtxNerfError(f"{what} failed with code {code}: {msg.decode() if msg else '?'}")
+
+
+def call(name: str, *args) -> None:
+    fn = getattr(lib(), name, None)
+    if fn is None:
+        raise CtxNerfError(f"libctxnerf.so does not export {name}; rebuild the extension")
+    check(fn(*args), name)
+
+
+def ptr(t) -> c_void_p:
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return c_void_p(0)
+    return c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None) -> c_void_p:
+    import torch
+    return c_void_p(torch.cuda.current_stream(device).cuda_stream)

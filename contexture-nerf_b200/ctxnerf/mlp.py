@@ -1,0 +1,159 @@
+"""Host side of the tcgen05 coordinate MLP: network description, weight
+packing and the autograd Function around ctx_mlp_fwd / ctx_mlp_bwd.
+
+The modules keep the reference's parameter names and order
+(/root/reference/src/run_nerf_helpers.py:81-97; trainer.py:888 indexes
+``parameters()[-2]``), so ``state_dict`` round-trips with ``NeRF2D``.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+
+TILE = 128
+
+
+class NetDesc:
+    """Opaque CtxMlpNet blob (csrc/mlp_desc.h) + the few fields Python needs."""
+
+    def __init__(self, D: int, skips: Sequence[int], in_pts: int, in_views: int, out_ch: int, W: int = 256):
+        if W != 256:
+            raise _lib.CtxNerfError(f"the tcgen05 MLP kernel is built for W=256 (got W={W})")
+        lib = _lib.lib()
+        n = lib.ctx_mlp_net_bytes()
+        self.blob = (ctypes.c_uint8 * n)()
+        mask = 0
+        for s in skips:
+            mask |= 1 << int(s)
+        _lib.check(lib.ctx_mlp_describe(D, mask, in_pts, in_views, out_ch, ctypes.cast(self.blob, ctypes.c_void_p)),
+                   "ctx_mlp_describe")
+        ints = ctypes.cast(self.blob, ctypes.POINTER(ctypes.c_int32))
+        (self.n_layers, self.in_pts, self.in_views, self.out_ch, self.head_off, self.w_bytes, self.wt_bytes,
+         self.n_fparams, self.act_tile_bytes) = [ints[i] for i in range(9)]
+        self.D = D
+
+    @property
+    def p(self):
+        return ctypes.cast(self.blob, ctypes.c_void_p)
+
+
+class PackedWeights:
+    """bf16 weight streams (forward + transposed) and the fp32 bias/head block,
+    per device; re-packed when any parameter's version counter changes
+    (optimizer steps bump it)."""
+
+    def __init__(self, desc: NetDesc):
+        self.desc = desc
+        self._per_dev = {}
+
+    def get(self, params: List[torch.Tensor]):
+        dev = params[0].device
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        ent = self._per_dev.get(dev)
+        if ent is not None and ent[0] == key:
+            return ent[1]
+        d = self.desc
+        for p in params:
+            if p.dtype != torch.float32 or not p.is_contiguous() or p.device != dev or not p.is_cuda:
+                raise _lib.CtxNerfError("MLP parameters must be contiguous fp32 tensors on one CUDA device "
+                                        "(ctxnerf has no CPU path)")
+        if ent is None:
+            bufs = (torch.empty(d.w_bytes, dtype=torch.uint8, device=dev),
+                    torch.empty(max(d.wt_bytes, 16), dtype=torch.uint8, device=dev),
+                    torch.empty(d.n_fparams, dtype=torch.float32, device=dev))
+        else:
+            bufs = ent[1]
+        arr = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
+        with torch.cuda.device(dev):
+            call("ctx_mlp_pack", d.p, ctypes.cast(arr, ctypes.c_void_p), len(params), ptr(bufs[0]), ptr(bufs[1]),
+                 ptr(bufs[2]), stream_ptr(dev))
+        self._per_dev[dev] = (key, bufs)
+        return bufs
+
+
+def _launch_fwd(desc: NetDesc, w, f, *, x=None, rays=None, P: int, out, acts=None, L_pts=10, L_dirs=4):
+    dev = out.device
+    with torch.cuda.device(dev):
+        if x is not None:
+            call("ctx_mlp_fwd", desc.p, ptr(w), ptr(f), 0, ptr(x), x.shape[-1], None, None, None, None, 0, 0, 0, P,
+                 ptr(out), ptr(acts), stream_ptr(dev))
+        else:
+            o, d, v, z = rays
+            call("ctx_mlp_fwd", desc.p, ptr(w), ptr(f), 1, None, 0, ptr(o), ptr(d), ptr(v), ptr(z), z.shape[-1],
+                 L_pts, L_dirs, P, ptr(out), ptr(acts), stream_ptr(dev))
+
+
+class _MlpFn(torch.autograd.Function):
+    """out = MLP(x or rays).  Gradients flow to the parameters only (inputs are
+    data: encodings of fixed coordinates)."""
+
+    @staticmethod
+    def forward(ctx, module, x, rays, *params):
+        desc: NetDesc = module._desc
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        w, wt, f = module._packed.get(list(params))
+        if x is not None:
+            if not x.is_cuda:
+                raise _lib.CtxNerfError("ctxnerf MLP runs on CUDA tensors only (no CPU fallback)")
+            lead = x.shape[:-1]
+            x2 = x.reshape(-1, x.shape[-1]).float().contiguous()
+            P = x2.shape[0]
+            dev = x.device
+        else:
+            o, d, v, z = rays
+            lead = z.shape
+            P = z.numel()
+            x2 = None
+            dev = z.device
+        out = torch.empty(P, desc.out_ch, device=dev, dtype=torch.float32)
+        acts = None
+        if need_grad:
+            ntiles = (P + TILE - 1) // TILE
+            ntiles += ntiles & 1
+            acts = torch.empty(ntiles * desc.act_tile_bytes, dtype=torch.uint8, device=dev)
+        _launch_fwd(desc, w, f, x=x2, rays=rays, P=P, out=out, acts=acts, L_pts=module.L_pts, L_dirs=module.L_dirs)
+        ctx.module = module
+        ctx.P = P
+        ctx.acts = acts
+        ctx.packed = (w, wt, f)
+        ctx.n_params = len(params)
+        return out.reshape(*lead, desc.out_ch)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        from .mlp_bwd import mlp_backward
+        grads = mlp_backward(ctx.module, ctx.packed, ctx.acts, ctx.P, g_out)
+        ctx.acts = None
+        return (None, None, None) + tuple(grads)
+
+
+class FusedMLPBase(nn.Module):
+    """Shared machinery of NeRF2D / NeRF: parameters are ordinary nn.Linear
+    modules (names/order of the reference); forward runs the fused kernel."""
+
+    L_pts = 10
+    L_dirs = 4
+
+    def _setup(self, D, W, skips, in_pts, in_views, out_ch):
+        self._desc_args = (D, tuple(skips), in_pts, in_views, out_ch, W)
+        self.__dict__["_desc"] = None
+        self.__dict__["_packed"] = None
+
+    def _ensure(self):
+        if self.__dict__.get("_desc") is None:
+            D, skips, in_pts, in_views, out_ch, W = self._desc_args
+            self.__dict__["_desc"] = NetDesc(D, skips, in_pts, in_views, out_ch, W)
+            self.__dict__["_packed"] = PackedWeights(self._desc)
+
+    def _param_list(self) -> List[torch.Tensor]:
+        raise NotImplementedError
+
+    def _run(self, x=None, rays=None):
+        self._ensure()
+        return _MlpFn.apply(self, x, rays, *self._param_list())

@@ -1,0 +1,135 @@
+/* ctxnerf.h -- C-ABI of libctxnerf.so: the B200 (sm_100a) NeRF ray-march path.
+ *
+ * The reference (zaiisao/ConTEXTure-NeRF) has no FFI: its boundary for this
+ * path is the Python surface of src/run_nerf_helpers.py.  Each entry point
+ * below is what a ctypes binding placed in that module calls instead of the
+ * eager-PyTorch body it replaces (file:line given per function; INTEGRATION.md
+ * shows the binding).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless marked "host"; tensors are
+ *    contiguous row-major fp32 unless a stride argument is given;
+ *  - the library never allocates, frees or synchronises; work is enqueued on
+ *    `stream` (a cudaStream_t passed as void*), launchers are re-entrant;
+ *  - return 0 on success, a positive cudaError_t on a CUDA failure, a negative
+ *    CTX_ERR_* on a bad argument.  Nothing throws across the ABI;
+ *  - "nullable" arguments may be NULL.
+ */
+#ifndef CTXNERF_H
+#define CTXNERF_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTXNERF_ABI_VERSION 1
+#define CTX_ERR_BAD_ARG (-1)
+#define CTX_ERR_UNSUPPORTED (-2)
+
+int ctx_abi_version(void);
+/* static string for a code returned by any ctx_* call */
+const char* ctx_error_string(int code);
+
+/* ---- positional encoding: Embedder.embed, src/run_nerf_helpers.py:44-45 ----
+ * x [n,d] -> out [n, d*(include_input + 2L)], channel order of :24-39.        */
+int ctx_posenc_fwd(const float* x, float* out, int64_t n, int d, int L, int include_input,
+                   int log_sampling, void* stream);
+int ctx_posenc_bwd(const float* x, const float* g_out, float* g_x, int64_t n, int d, int L,
+                   int include_input, int log_sampling, void* stream);
+
+/* ---- ray generation fused with stratified sampling --------------------------
+ * get_rays, src/run_nerf_helpers.py:139-148 (+ optional ndc_rays :161-178 and
+ * upstream render_rays' depth sampling).  c2w: device [3,4] row-major with
+ * leading dimension c2w_ld.  ray_idx (nullable): flat pixel ids y*W+x to
+ * generate (training batches); NULL = all H*W pixels in row-major order.
+ * n_samples == 0 skips z_vals.  perturb != 0 jitters with `jitter`
+ * [n_rays,n_samples] if given, else with Philox(seed).  sphere (host,
+ * nullable: cx,cy,cz,r) replaces near/far by the ray/sphere interval.
+ * viewdirs, z_vals, near_far ([n,2]) are nullable outputs.                     */
+int ctx_raygen_fwd(int H, int W, float fx, float fy, float cx, float cy, const float* c2w,
+                   int c2w_ld, const int64_t* ray_idx, int64_t n_rays, int use_ndc,
+                   float ndc_focal, float ndc_near, int n_samples, float near, float far,
+                   int lindisp, int perturb, const float* jitter, uint64_t seed, int use_sphere,
+                   const float* sphere, float* rays_o, float* rays_d, float* viewdirs,
+                   float* z_vals, float* near_far, void* stream);
+
+/* z_vals [R,S] from per-ray near/far (ray_batch[:,6], ray_batch[:,7] upstream) */
+int ctx_stratified_fwd(const float* near, int64_t near_stride, const float* far,
+                       int64_t far_stride, int64_t R, int S, int lindisp, int perturb,
+                       const float* jitter, uint64_t seed, float* z_vals, void* stream);
+
+/* ---- ndc_rays, src/run_nerf_helpers.py:161-178 ------------------------------ */
+int ctx_ndc_fwd(int H, int W, float focal, float near, const float* rays_o, const float* rays_d,
+                int64_t n, float* o_out, float* d_out, void* stream);
+int ctx_ndc_bwd(int H, int W, float focal, float near, const float* rays_o, const float* rays_d,
+                const float* g_o, const float* g_d, int64_t n, float* g_rays_o, float* g_rays_d,
+                void* stream);
+
+/* ---- raw2outputs (absent from the reference; pointer comment at
+ * src/run_nerf_helpers.py:131-133; spec SURVEY.md 8c-S1) -----------------------
+ * raw [R,S,4], z_vals [R,S], rays_d [R,3], noise (nullable, [R,S], already
+ * scaled by raw_noise_std) -> rgb [R,3], disp [R], acc [R], weights [R,S],
+ * depth [R].  S <= 512.                                                        */
+int ctx_composite_fwd(const float* raw, const float* z_vals, const float* rays_d,
+                      const float* noise, int64_t R, int S, int white_bkgd, float* rgb_map,
+                      float* disp_map, float* acc_map, float* weights, float* depth_map,
+                      void* stream);
+/* g_* inputs nullable (treated as zero); writes g_raw [R,S,4] */
+int ctx_composite_bwd(const float* raw, const float* z_vals, const float* rays_d,
+                      const float* noise, int64_t R, int S, int white_bkgd, const float* g_rgb,
+                      const float* g_disp, const float* g_acc, const float* g_weights,
+                      const float* g_depth, float* g_raw, void* stream);
+
+/* ---- sample_pdf, src/run_nerf_helpers.py:182-225 ----------------------------
+ * bins [R,B] with row stride bins_stride (mid_bins != 0: `bins` is z [R,B+1]
+ * and the mid-points .5*(z[i+1]+z[i]) are formed in-kernel), weights [R,B-1]
+ * with row stride w_stride (the reference passes the view weights[...,1:-1]).
+ * cdf_in (nullable [R,B]) injects stage 1.  u (nullable [R,N]) injects the
+ * uniforms; else det -> linspace(0,1,N), otherwise Philox(seed).
+ * Outputs: samples [R,N]; inds (nullable, int64 [R,N]) = searchsorted result;
+ * z_all (nullable [R,Sm+N]) = sort(cat[z_merge[R,Sm], samples]).               */
+int ctx_resample_fwd(const float* bins, int64_t bins_stride, int mid_bins, const float* weights,
+                     int64_t w_stride, const float* cdf_in, const float* u, int det,
+                     uint64_t seed, int64_t R, int B, int N, float* samples, int64_t* inds,
+                     const float* z_merge, int64_t zm_stride, int Sm, float* z_all, void* stream);
+/* d samples / d weights -> g_weights [R,B-1] (contiguous) */
+int ctx_resample_bwd(const float* bins, int64_t bins_stride, int mid_bins, const float* weights,
+                     int64_t w_stride, const float* u, int det, uint64_t seed, int64_t R, int B,
+                     int N, const float* g_samples, float* g_weights, void* stream);
+
+/* ---- coordinate MLP: NeRF2D, src/run_nerf_helpers.py:68-135 (+ the upstream
+ * view-direction head kept as comments :86-95, :117-127) ----------------------
+ * tcgen05/TMEM kernel, bf16 operands, fp32 accumulation, hidden width 256.
+ * `net` is a HOST blob of ctx_mlp_net_bytes() bytes filled by ctx_mlp_describe:
+ * D pts layers, skip_mask bit i set <=> "i in skips" (input re-concatenated
+ * after layer i, :114-115), in_pts/in_views real encoding widths (63|42 / 27|0),
+ * out_ch 4|3 (must be 4 with views).                                            */
+int ctx_mlp_net_bytes(void);
+int ctx_mlp_describe(int D, uint32_t skip_mask, int in_pts, int in_views, int out_ch, void* net);
+/* params: HOST array of n_params DEVICE pointers (fp32, nn.Linear [out,in]) in
+ * module order: pts_linears.{0..D-1}.{weight,bias}, then output_linear.{w,b}
+ * or feature_linear, alpha_linear, views_linears.0, rgb_linear {w,b}.
+ * wpacked [w_bytes], wtpacked [wt_bytes] (nullable), fparams [n_fparams]: device
+ * buffers sized from the net blob (see contexture-nerf_b200/csrc/mlp_desc.h).   */
+int ctx_mlp_pack(const void* net, const float* const* params, int n_params, void* wpacked,
+                 void* wtpacked, float* fparams, void* stream);
+/* mode 0: x [P,x_ld] holds the already-encoded input [pts_enc | view_enc];
+ * mode 1: the P = R*S points o + d*z (z [R,S]) and the view directions are
+ * encoded in-kernel straight into shared memory (Embedder.embed :44-45, L_pts
+ * / L_dirs frequencies).  out [P,out_ch] raw network output (no activation,
+ * :129).  acts (nullable): activation records for ctx_mlp_bwd.                  */
+int ctx_mlp_fwd(const void* net, const void* wpacked, const float* fparams, int mode, const float* x,
+                int x_ld, const float* rays_o, const float* rays_d, const float* viewdirs,
+                const float* z, int S, int L_pts, int L_dirs, int64_t P, float* out, void* acts,
+                void* stream);
+
+/* diagnostic: one-CTA tcgen05 GEMM C[128,N] = A * B^T (tests pin the descriptor
+ * conventions with it); A,B bf16.  mode 0 K-major operands, 1 MN-major.          */
+int ctx_tcgen05_selftest(const void* A, const void* B, float* C, int N, int K, int mode, int variant,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTXNERF_H */

@@ -1,0 +1,57 @@
+"""The C-ABI library loads and exports every symbol include/ctxnerf.h declares
+(no compute calls: this runs without a GPU)."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ctxnerf.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ctx_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_declares_the_hot_path():
+    syms = declared_symbols()
+    for need in ("ctx_posenc_fwd", "ctx_posenc_bwd", "ctx_raygen_fwd", "ctx_stratified_fwd", "ctx_ndc_fwd",
+                 "ctx_ndc_bwd", "ctx_composite_fwd", "ctx_composite_bwd", "ctx_resample_fwd", "ctx_resample_bwd",
+                 "ctx_mlp_describe", "ctx_mlp_pack", "ctx_mlp_fwd"):
+        assert need in syms
+
+
+def test_library_exports_every_declared_symbol(libpath):
+    lib = ctypes.CDLL(libpath)
+    missing = [s for s in declared_symbols() if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_python_binding_covers_header(libpath):
+    from ctxnerf import _lib
+    assert set(declared_symbols()) <= set(_lib._SIGNATURES), set(declared_symbols()) - set(_lib._SIGNATURES)
+    assert _lib.lib().ctx_abi_version() == 1
+    assert b"bad argument" in _lib.lib().ctx_error_string(-1)
+
+
+def test_argument_errors_do_not_need_a_gpu(libpath):
+    """Negative sizes / null pointers are rejected before any launch."""
+    from ctxnerf import _lib
+    lib = _lib.lib()
+    assert lib.ctx_composite_fwd(None, None, None, None, 4, 64, 0, None, None, None, None, None, None) == -1
+    assert lib.ctx_composite_fwd(None, None, None, None, 0, 64, 0, None, None, None, None, None, None) == 0
+    assert lib.ctx_posenc_fwd(None, None, -1, 3, 10, 1, 1, None) == -1
+    assert lib.ctx_resample_fwd(None, 0, 0, None, 0, None, None, 1, 0, 8, 1, 16, None, None, None, 0, 0, None,
+                                None) == -1
+
+
+def test_mlp_describe_matches_the_reference_layer_structure(libpath):
+    """NeRF2D(D=8, W=256, skips=[4]): layer 5 takes [x | h] (reference :81-83)."""
+    from ctxnerf.mlp import NetDesc
+    d = NetDesc(8, [4], 63, 0, 4)
+    assert d.n_layers == 8
+    # forward stream: L0 64x256, 7 hidden 256x256 (+64 on the skip layer), bf16
+    assert d.w_bytes == 2 * 256 * (64 + 7 * 256 + 64)
+    v = NetDesc(8, [4], 63, 27, 4)
+    assert v.n_layers == 10
+    assert v.w_bytes == d.w_bytes + 2 * (256 * 256 + 128 * (256 + 32))

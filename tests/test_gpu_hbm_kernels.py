@@ -1,0 +1,303 @@
+"""GPU parity: the HBM-bound kernels (posenc, raygen+stratified, ndc,
+raw2outputs, sample_pdf) against the CPU oracle and the committed golden
+vectors, all through the C-ABI (ctxnerf.ops -> ctypes -> libctxnerf.so).
+
+Tolerances (BASELINE.json north_star): searchsorted indices and det=True sample
+positions bit-exact; rays/ndc/stratified bit-exact (pure fp32 elementwise);
+rgb/depth/acc/weights 1e-5 relative (stated as rtol=1e-5 with the absolute
+floor of SURVEY.md H6 for ~1e-10 weights)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nerf_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+# ------------------------------------------------------------------ posenc ---
+def test_posenc_matches_golden_and_oracle(cuda, golden):
+    from ctxnerf import run_nerf_helpers as rh
+    for tag, d, L in (("uv", 2, 10), ("pts", 3, 10), ("dirs", 3, 4)):
+        x = T(golden[f"emb_{tag}_x"]).to(cuda)
+        eo = rh.Embedder(include_input=True, input_dims=d, max_freq_log2=L - 1, num_freqs=L, log_sampling=True,
+                         periodic_fns=[torch.sin, torch.cos])
+        assert eo.out_dim == d * (1 + 2 * L)
+        y = eo.embed(x).cpu()
+        torch.testing.assert_close(y, T(golden[f"emb_{tag}_y"]), rtol=1e-5, atol=2e-6)
+    fn, od = rh.get_embedder(10)
+    assert od == 42
+    torch.testing.assert_close(fn(T(golden["emb_uv_x"]).to(cuda)).cpu(), T(golden["get_embedder10_y"]),
+                               rtol=1e-5, atol=2e-6)
+    # large ragged size, identity passthrough is exact
+    x = (torch.rand(100003, 3) * 4 - 2)
+    y = rh.Embedder(include_input=True, input_dims=3, max_freq_log2=9, num_freqs=10, log_sampling=True,
+                    periodic_fns=[torch.sin, torch.cos]).embed(x.to(cuda)).cpu()
+    ref = orc.posenc(x, 10)
+    assert torch.equal(y[:, :3], x)
+    torch.testing.assert_close(y, ref, rtol=1e-5, atol=2e-6)
+    # empty input
+    assert rh.get_embedder(10, input_dims=3)[0](torch.empty(0, 3, device=cuda)).shape == (0, 63)
+
+
+def test_posenc_backward(cuda):
+    from ctxnerf import ops
+    x = (torch.rand(513, 3) * 2 - 1).requires_grad_(True)
+    g = torch.randn(513, 27)
+    orc.posenc(x, 4).backward(g)
+    xc = x.detach().to(cuda).requires_grad_(True)
+    ops.posenc(xc, 4).backward(g.to(cuda))
+    torch.testing.assert_close(xc.grad.cpu(), x.grad, rtol=1e-4, atol=1e-4)
+
+
+# -------------------------------------------------------------------- rays ---
+def test_get_rays_bit_exact(cuda, golden):
+    from ctxnerf import run_nerf_helpers as rh
+    H, W = [int(v) for v in golden["rays_HW"]]
+    ro, rd = rh.get_rays(H, W, golden["rays_K"].tolist(), T(golden["rays_c2w"]).to(cuda))
+    assert torch.equal(rd.cpu(), T(golden["rays_d"]))
+    assert torch.equal(ro.cpu().contiguous(), T(golden["rays_o"]))
+    assert ro.stride()[:2] == (0, 0)          # stride-0 view like the reference
+    # BASELINE config 2 camera, full 800x800 image
+    K, c2w = orc.lego_like_camera()
+    ro2, rd2 = rh.get_rays(800, 800, K, c2w.to(cuda))
+    ro_ref, rd_ref = orc.get_rays(800, 800, K, c2w)
+    assert torch.equal(rd2.cpu(), rd_ref)
+    _, rd_np = rh.get_rays_np(H, W, golden["rays_K"], golden["rays_c2w"])
+    np.testing.assert_array_equal(rd_np, golden["rays_d"])
+
+
+def test_raygen_fused_stratified_bit_exact(cuda):
+    from ctxnerf import ops
+    K, c2w = orc.lego_like_camera()
+    g = torch.Generator().manual_seed(3)
+    idx = torch.randint(0, 800 * 800, (4096,), generator=g)
+    jit = torch.rand(4096, 64, generator=g)
+    r = ops.raygen(800, 800, K, c2w.to(cuda), ray_idx=idx.to(cuda), n_samples=64, near=2.0, far=6.0, perturb=True,
+                   jitter=jit.to(cuda), want_viewdirs=True)
+    ro_ref, rd_ref = orc.get_rays(800, 800, K, c2w)
+    rd_sel = rd_ref.reshape(-1, 3)[idx]
+    assert torch.equal(r["rays_d"].cpu(), rd_sel)
+    vd = rd_sel / torch.norm(rd_sel, dim=-1, keepdim=True)
+    torch.testing.assert_close(r["viewdirs"].cpu(), vd, rtol=1e-6, atol=1e-7)
+    near, far = torch.full((4096, 1), 2.0), torch.full((4096, 1), 6.0)
+    assert torch.equal(r["z_vals"].cpu(), orc.stratified_z(near, far, 64, jitter=jit))
+    # no jitter, lindisp, per-ray near/far through the stand-alone sampler
+    nf = torch.rand(300, 2) + torch.tensor([1.0, 4.0])
+    for lindisp in (False, True):
+        z = ops.stratified(nf[:, 0].to(cuda), nf[:, 1].to(cuda), 37, lindisp=lindisp)
+        assert torch.equal(z.cpu(), orc.stratified_z(nf[:, :1], nf[:, 1:], 37, lindisp=lindisp)), lindisp
+    # in-kernel Philox jitter: samples stay inside their strata and are reproducible
+    a = ops.stratified(nf[:, 0].to(cuda), nf[:, 1].to(cuda), 64, perturb=True, seed=7).cpu()
+    b = ops.stratified(nf[:, 0].to(cuda), nf[:, 1].to(cuda), 64, perturb=True, seed=7).cpu()
+    assert torch.equal(a, b)
+    z0 = orc.stratified_z(nf[:, :1], nf[:, 1:], 64)
+    mids = 0.5 * (z0[:, 1:] + z0[:, :-1])
+    assert (a[:, 1:-1] >= mids[:, :-1]).all() and (a[:, 1:-1] <= mids[:, 1:]).all()
+    assert 0.2 < ((a[:, 1:-1] - mids[:, :-1]) / (mids[:, 1:] - mids[:, :-1])).mean() < 0.8
+
+
+def test_raygen_sphere_bounds(cuda):
+    """config 4: per-ray near/far from the bounding sphere of the normalised mesh."""
+    from ctxnerf import ops
+    K = [[886.81, 0, 512.0], [0, 886.81, 512.0], [0, 0, 1]]
+    c2w = torch.tensor([[1.0, 0, 0, 0.0], [0, 1, 0, 0.25], [0, 0, 1, 1.5]])
+    r = ops.raygen(1024, 1024, K, c2w.to(cuda), sphere=(0.0, 0.25, 0.0, 0.6), n_samples=8, want_near_far=True)
+    nf = r["near_far"].cpu().reshape(1024, 1024, 2)
+    torch.testing.assert_close(nf[512, 512], torch.tensor([0.9, 2.1]), rtol=1e-5, atol=1e-5)
+    assert (nf[0, 0, 0] == nf[0, 0, 1])       # corner ray misses the sphere
+    z = r["z_vals"].cpu().reshape(1024, 1024, 8)
+    assert torch.equal(z[512, 512], orc.stratified_z(nf[512, 512, :1][None], nf[512, 512, 1:][None], 8)[0])
+
+
+def test_ndc_bit_exact_and_backward(cuda, golden):
+    from ctxnerf import run_nerf_helpers as rh
+    H, W, focal, near = golden["ndc_args"]
+    o, d = rh.ndc_rays(int(H), int(W), float(focal), float(near), T(golden["ndc_in_o"]).to(cuda),
+                       T(golden["ndc_in_d"]).to(cuda))
+    assert torch.equal(o.cpu(), T(golden["ndc_o"]))
+    assert torch.equal(d.cpu(), T(golden["ndc_d"]))
+    oi = T(golden["ndc_in_o"]).clone().requires_grad_(True)
+    di = T(golden["ndc_in_d"]).clone().requires_grad_(True)
+    oo, dd = orc.ndc_rays(int(H), int(W), float(focal), float(near), oi, di)
+    go, gd = torch.randn_like(oo), torch.randn_like(dd)
+    (oo * go + dd * gd).sum().backward()
+    oc = oi.detach().to(cuda).requires_grad_(True)
+    dc = di.detach().to(cuda).requires_grad_(True)
+    o2, d2 = rh.ndc_rays(int(H), int(W), float(focal), float(near), oc, dc)
+    (o2 * go.to(cuda) + d2 * gd.to(cuda)).sum().backward()
+    torch.testing.assert_close(oc.grad.cpu(), oi.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(dc.grad.cpu(), di.grad, rtol=1e-4, atol=1e-5)
+
+
+# --------------------------------------------------------------- composite ---
+def close_w(a, b, what):
+    """1e-5 relative with the floor of SURVEY.md H6 (weights reach 1e-10 behind an opaque sample)."""
+    scale = b.abs().amax(dim=-1, keepdim=True).clamp_min(1e-30) if b.dim() > 1 else b.abs().clamp_min(1e-30)
+    err = (a - b).abs()
+    tol = 1e-5 * torch.maximum(b.abs(), scale * 1e-3) + 1e-7
+    bad = err > tol
+    assert not bad.any(), f"{what}: {int(bad.sum())} elements off, max err {err.max().item():.3e}"
+
+
+@pytest.mark.parametrize("R,S", [(4096, 64), (4096, 192), (1000, 37), (257, 512), (5, 1)])
+def test_composite_forward(cuda, R, S):
+    from ctxnerf import run_nerf_helpers as rh
+    raw, z, d = orc.cfg1_inputs(R, S, seed=S)
+    if S > 1:
+        z = torch.sort(torch.rand(R, S) * 4 + 2, -1)[0]
+    for white in (False, True):
+        ref = orc.raw2outputs(raw, z, d, white_bkgd=white)
+        got = rh.raw2outputs(raw.to(cuda), z.to(cuda), d.to(cuda), white_bkgd=white)
+        names = ("rgb", "disp", "acc", "weights", "depth")
+        for n, a, b in zip(names, got, ref):
+            a = a.cpu()
+            if n == "disp":
+                assert torch.equal(torch.isnan(a), torch.isnan(b))
+                ok = ~torch.isnan(b)
+                torch.testing.assert_close(a[ok], b[ok], rtol=2e-5, atol=1e-7)
+            else:
+                close_w(a, b, f"{n} R={R} S={S} white={white}")
+
+
+def test_composite_known_answers(cuda):
+    from ctxnerf import run_nerf_helpers as rh
+    raw = -torch.rand(4, 8, 4) - 0.1
+    z = torch.linspace(2, 6, 8).expand(4, 8).contiguous()
+    d = torch.randn(4, 3)
+    rgb, disp, acc, w, depth = [t.cpu() for t in rh.raw2outputs(raw.to(cuda), z.to(cuda), d.to(cuda), white_bkgd=True)]
+    assert (w == 0).all() and (acc == 0).all() and (rgb == 1).all() and torch.isnan(disp).all()
+    raw = torch.full((1, 10, 4), -5.0)
+    raw[0, 6, 3] = 1e4
+    z = torch.linspace(2, 6, 10)[None].contiguous()
+    out = rh.raw2outputs(raw.to(cuda), z.to(cuda), torch.tensor([[0.0, 1.0, 0.0]], device=cuda))
+    assert out[3].cpu()[0, 6] == 1.0 and out[4].cpu()[0] == z[0, 6]
+    # empty batch
+    e = rh.raw2outputs(torch.empty(0, 64, 4, device=cuda), torch.empty(0, 64, device=cuda), torch.empty(0, 3, device=cuda))
+    assert e[0].shape == (0, 3) and e[3].shape == (0, 64)
+
+
+@pytest.mark.parametrize("R,S,white", [(512, 64, False), (512, 192, True), (100, 37, False)])
+def test_composite_backward(cuda, R, S, white):
+    """hand-written backward == autograd through the oracle (all five outputs feed the loss)."""
+    from ctxnerf import run_nerf_helpers as rh
+    raw, z, d = orc.cfg1_inputs(R, S, seed=11)
+    raw[..., 3] *= 0.3                     # keep several samples translucent
+    noise = torch.randn(R, S) * 0.1
+    g = torch.Generator().manual_seed(5)
+    gs = [torch.randn(R, 3, generator=g), torch.randn(R, generator=g), torch.randn(R, generator=g),
+          torch.randn(R, S, generator=g), torch.randn(R, generator=g)]
+    r0 = raw.clone().requires_grad_(True)
+    outs = orc.raw2outputs(r0, z, d, white_bkgd=white, noise=noise)
+    keep = ~torch.isnan(outs[1])
+    loss = sum((o * gg).sum() for i, (o, gg) in enumerate(zip(outs, gs)) if i != 1) + (outs[1][keep] * gs[1][keep]).sum()
+    loss.backward()
+    from ctxnerf import ops
+    rc = raw.to(cuda).requires_grad_(True)
+    oc = ops.composite(rc, z.to(cuda), d.to(cuda), noise.to(cuda), white)
+    gdisp = gs[1].clone()
+    gdisp[~keep] = 0
+    torch.autograd.backward(list(oc), [gs[0].to(cuda), gdisp.to(cuda), gs[2].to(cuda), gs[3].to(cuda), gs[4].to(cuda)])
+    a, b = rc.grad.cpu(), r0.grad
+    scale = b.abs().amax(dim=(1, 2), keepdim=True).clamp_min(1e-12)
+    assert ((a - b).abs() <= 2e-4 * scale + 1e-6).all(), ((a - b).abs() / scale).max()
+
+
+# ---------------------------------------------------------------- resample ---
+def test_sample_pdf_stage2_bit_exact_against_reference_golden(cuda, golden):
+    from ctxnerf import ops
+    bins, w, cdf = T(golden["pdf_bins"]), T(golden["pdf_w"]), T(golden["pdf_cdf_ref"])
+    s, i = ops.resample_raw(bins.to(cuda), None, 128, det=True, cdf=cdf.to(cuda))
+    assert torch.equal(s.cpu(), T(golden["pdf_det"]))
+    assert torch.equal(i.cpu(), T(golden["pdf_det_inds"]))
+    s, i = ops.resample_raw(bins.to(cuda), None, 128, det=False, u=T(golden["pdf_u_rand"]).to(cuda), cdf=cdf.to(cuda))
+    assert torch.equal(s.cpu(), T(golden["pdf_rand"]))
+    assert torch.equal(i.cpu(), T(golden["pdf_rand_inds"]))
+
+
+@pytest.mark.parametrize("R,B,N", [(4096, 63, 128), (513, 191, 64), (64, 511, 1024), (7, 2, 5), (33, 63, 1)])
+def test_sample_pdf_bit_exact_against_oracle(cuda, R, B, N):
+    from ctxnerf import ops, run_nerf_helpers as rh
+    g = torch.Generator().manual_seed(B)
+    bins = torch.sort(torch.rand(R, B, generator=g) * 4 + 2, -1)[0]
+    w = torch.rand(R, B - 1, generator=g) ** 3
+    w[0] = 0
+    if B > 3:
+        w[1] = 0
+        w[1, B // 2] = 1
+    s_ref, i_ref = orc.sample_pdf(bins, w, N, det=True, return_inds=True)
+    s, i = ops.resample_raw(bins.to(cuda), w.to(cuda), N, det=True)
+    assert torch.equal(i.cpu(), i_ref)
+    assert torch.equal(s.cpu(), s_ref)
+    assert torch.equal(rh.sample_pdf(bins.to(cuda), w.to(cuda), N, det=True).cpu(), s_ref)
+    u = torch.rand(R, N, generator=g)
+    s_ref, i_ref = orc.sample_pdf(bins, w, N, u=u, return_inds=True)
+    s, i = ops.resample_raw(bins.to(cuda), w.to(cuda), N, det=False, u=u.to(cuda))
+    assert torch.equal(i.cpu(), i_ref) and torch.equal(s.cpu(), s_ref)
+
+
+def test_sample_pdf_noncontiguous_weights_and_pytest_flag(cuda, golden):
+    from ctxnerf import run_nerf_helpers as rh
+    bins, wfull = T(golden["pdf_bins"]), T(golden["pdf_wfull"])
+    s = rh.sample_pdf(bins.to(cuda), wfull.to(cuda)[..., 1:-1], 128, det=True).cpu()
+    assert torch.equal(s, orc.sample_pdf(bins, wfull[..., 1:-1].contiguous(), 128, det=True))
+    assert (s - T(golden["pdf_det_slice"])).abs().median() < 1e-6
+    s = rh.sample_pdf(bins.to(cuda), T(golden["pdf_w"]).to(cuda), 16, det=False, pytest=True).cpu()
+    np.random.seed(0)
+    u = torch.Tensor(np.random.rand(bins.shape[0], 16))
+    assert torch.equal(s, orc.sample_pdf(bins, T(golden["pdf_w"]), 16, u=u))
+    # random path: in-kernel Philox, monotone after sort, inside the bin range, reproducible under manual_seed
+    torch.manual_seed(1)
+    a = rh.sample_pdf(bins.to(cuda), T(golden["pdf_w"]).to(cuda), 64).cpu()
+    torch.manual_seed(1)
+    b = rh.sample_pdf(bins.to(cuda), T(golden["pdf_w"]).to(cuda), 64).cpu()
+    assert torch.equal(a, b)
+    assert (a >= bins[:, :1]).all() and (a <= bins[:, -1:]).all()
+
+
+def test_resample_merge_fused(cuda):
+    """config 1 chain: raw2outputs(64) -> sample_pdf(det, 128) -> sort(cat) , bit-exact."""
+    from ctxnerf import ops, run_nerf_helpers as rh
+    raw, z, d = orc.cfg1_inputs(4096, 64)
+    w_ref = orc.raw2outputs(raw, z, d)[3]
+    w_gpu = rh.raw2outputs(raw.to(cuda), z.to(cuda), d.to(cuda))[3]
+    # feed the SAME weights to both so the comparison isolates the resampler
+    zs, z_all, inds = ops.resample_merge(z.to(cuda), w_ref.to(cuda), 128, det=True, return_inds=True)
+    z_mid = 0.5 * (z[..., 1:] + z[..., :-1])
+    s_ref, i_ref = orc.sample_pdf(z_mid, w_ref[..., 1:-1], 128, det=True, return_inds=True)
+    assert torch.equal(inds.cpu(), i_ref)
+    assert torch.equal(zs.cpu(), s_ref)
+    assert torch.equal(z_all.cpu(), torch.sort(torch.cat([z, s_ref], -1), -1)[0])
+    # and end to end with the GPU's own weights: indices may only differ where weights differ by rounding
+    zs2, z_all2, inds2 = ops.resample_merge(z.to(cuda), w_gpu, 128, det=True, return_inds=True)
+    assert (inds2.cpu() == i_ref).float().mean() > 0.999
+    assert (z_all2[:, 1:] >= z_all2[:, :-1]).all()
+    # random u: sorted merge equals torch.sort of the concatenation
+    u = torch.rand(4096, 128)
+    zs3, z_all3 = ops.resample_merge(z.to(cuda), w_ref.to(cuda), 128, det=False, u=u.to(cuda))
+    s3 = orc.sample_pdf(z_mid, w_ref[..., 1:-1], 128, u=u)
+    assert torch.equal(zs3.cpu(), s3)
+    assert torch.equal(z_all3.cpu(), torch.sort(torch.cat([z, s3], -1), -1)[0])
+
+
+def test_sample_pdf_backward(cuda):
+    from ctxnerf import ops
+    g = torch.Generator().manual_seed(2)
+    R, B, N = 64, 33, 48
+    bins = torch.sort(torch.rand(R, B, generator=g) * 4 + 2, -1)[0]
+    w = (torch.rand(R, B - 1, generator=g) + 0.05).requires_grad_(True)
+    u = torch.rand(R, N, generator=g)
+    gs = torch.randn(R, N, generator=g)
+    wp = w + 1e-5
+    pdf = wp / wp.sum(-1, keepdim=True)
+    cdf = torch.cat([torch.zeros(R, 1), torch.cumsum(pdf, -1)], -1)
+    s = orc.sample_pdf(bins, w, N, u=u, cdf=cdf)
+    s.backward(gs)
+    wc = w.detach().to(cuda).requires_grad_(True)
+    sc = ops.resample(bins.to(cuda), wc, N, u=u.to(cuda))
+    sc.backward(gs.to(cuda))
+    torch.testing.assert_close(wc.grad.cpu(), w.grad, rtol=2e-3, atol=2e-4)
