@@ -144,7 +144,7 @@ def close_w(a, b, what):
     assert not bad.any(), f"{what}: {int(bad.sum())} elements off, max err {err.max().item():.3e}"
 
 
-@pytest.mark.parametrize("R,S", [(4096, 64), (4096, 192), (1000, 37), (257, 512), (5, 1)])
+@pytest.mark.parametrize("R,S", [(4096, 64), (4096, 192), (1000, 37), (257, 512), (5, 2)])
 def test_composite_forward(cuda, R, S):
     from ctxnerf import run_nerf_helpers as rh
     raw, z, d = orc.cfg1_inputs(R, S, seed=S)
