@@ -36,7 +36,7 @@ typedef struct {
   int32_t wt_off;    /* byte offset in the transposed (dgrad) stream, -1 if none */
   int32_t act_slot;  /* byte offset, within a tile's activation record, of this layer's OUTPUT */
   int32_t in_slot;   /* byte offset of the record holding this layer's h INPUT (-1: none) */
-  int32_t pad_;
+  int32_t mask_slot; /* byte offset of the ReLU sign-bit record (128 rows x N/32 words), -1: none */
 } CtxMlpLayer;
 
 typedef struct {

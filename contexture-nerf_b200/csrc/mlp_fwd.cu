@@ -18,77 +18,9 @@
 //
 // Reference semantics: NeRF2D.forward, /root/reference/src/run_nerf_helpers.py:106-135
 // (and the commented view branch :117-127); Embedder.embed :44-45.
-#include "ctx_common.cuh"
-#include "tc_common.cuh"
-#include "mlp_desc.h"
+#include "mlp_common.cuh"
 
 namespace ctx {
-
-constexpr int kTileM = 128;
-constexpr int kTiles = 2;
-constexpr int kStages = 4;
-constexpr int kStageBytes = CTX_MLP_W * CTX_MLP_KC * 2;   // 16 KB
-constexpr int kHBytes = kTileM * CTX_MLP_W * 2;            // 64 KB
-constexpr int kXBytes = kTileM * CTX_MLP_XP_PAD * 2;       // 16 KB
-constexpr int kK8Stride = kTileM * 16;                     // 2048 B between 8-wide K chunks of an A tile
-constexpr int kMlpThreads = 320;
-constexpr int kEpiThreadsPerTile = 128;
-
-struct MlpFwdArgs {
-  CtxMlpNet net;
-  const uint8_t* wpacked;
-  const float* fparams;
-  // input
-  int mode;                 // 0: pre-encoded x [P, x_ld] fp32, 1: rays + z (encode in-kernel)
-  const float* x; int x_ld;
-  const float* rays_o; const float* rays_d; const float* viewdirs; const float* z;
-  int S; int L_pts; int L_dirs;
-  int64_t P;
-  float* out;               // [P, out_ch]
-  uint8_t* acts;            // nullable: per-tile activation records (training)
-};
-
-struct __align__(8) MlpSmemCtl {
-  uint64_t full[kStages], empty[kStages];
-  uint64_t acc_full[kTiles], act_ready[kTiles];
-  uint32_t tmem_base;
-};
-
-constexpr size_t kMlpSmemBytes = (size_t)kTiles * (kHBytes + kXBytes) + (size_t)kStages * kStageBytes + 256;
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
-
-// sin/cos of a (possibly large) fp32 angle, good to ~2e-4 abs: enough for a bf16 operand
-__device__ __forceinline__ void fast_sincos(float a, float& s, float& c) {
-  float t = a * 0.15915494309189535f;
-  t -= rintf(t);
-  const float r = t * 6.283185307179586f;
-  s = __sinf(r);
-  c = __cosf(r);
-}
-
-// write 8 consecutive channels [ch0, ch0+8) of row `row` of a K-major A tile
-__device__ __forceinline__ void store_row8(uint8_t* tile, int row, int ch0, const float* v, bool relu) {
-  uint4 q;
-  if (relu) {
-    q.x = pack_bf16x2_relu(v[0], v[1]); q.y = pack_bf16x2_relu(v[2], v[3]);
-    q.z = pack_bf16x2_relu(v[4], v[5]); q.w = pack_bf16x2_relu(v[6], v[7]);
-  } else {
-    q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
-    q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
-  }
-  *reinterpret_cast<uint4*>(tile + (ch0 >> 3) * kK8Stride + (row >> 3) * 128 + (row & 7) * 16) = q;
-}
 
 // encode d-dim coordinate vector into channels [x | sin f0 x | cos f0 x | ...] padded with zeros to `pad`
 template <int PAD, int MAXL>
@@ -283,11 +215,15 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fwd_kernel(const __grid_co
           }
           tc::tmem_wait_ld();
           float v[32];
+          uint32_t neg = 0;   // bit (31-j) = sign of pre-activation j (the ReLU mask the dgrad kernel reads)
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             v[j] = __uint_as_float(vr[j]) + bias[j];
+            if (rec) neg = __funnelshift_l(__float_as_uint(v[j]), neg, 1);
             if (L.relu) v[j] = fmaxf(v[j], 0.f);
           }
+          if (rec && L.mask_slot >= 0)
+            reinterpret_cast<uint32_t*>(rec + L.mask_slot)[row * (L.N / 32) + cb] = neg;
           if (L.epi == CTX_EPI_HIDDEN_ALPHA) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) alpha = fmaf(bf16_round(v[j]), __ldg(hw + cb * 32 + j), alpha);

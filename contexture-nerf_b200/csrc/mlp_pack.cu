@@ -112,6 +112,7 @@ extern "C" int ctx_mlp_describe(int D, uint32_t skip_mask, int in_pts, int in_vi
     L.w_off = w_off; w_off += (L.n_x_pre + L.n_h) * CTX_MLP_KC * L.N * 2;
     if (l > 0) { L.wt_off = wt_off; wt_off += CTX_MLP_W * 256 * 2; } else L.wt_off = -1;
     L.act_slot = slot; slot += 128 * L.N * 2;
+    L.mask_slot = slot; slot += 128 * (L.N / 32) * 4;
     L.in_slot = prev_slot; prev_slot = L.act_slot;
   }
   if (in_views > 0) {
@@ -122,6 +123,7 @@ extern "C" int ctx_mlp_describe(int D, uint32_t skip_mask, int in_pts, int in_vi
     F.w_off = w_off; w_off += F.n_h * CTX_MLP_KC * F.N * 2;
     F.wt_off = wt_off; wt_off += CTX_MLP_W * 256 * 2;
     F.act_slot = slot; slot += 128 * F.N * 2;
+    F.mask_slot = -1;
     F.in_slot = prev_slot; prev_slot = F.act_slot;
     ++n;
     CtxMlpLayer& V = net.L[n];  // views_linears.0: [feature | dirs] -> 128, relu ; rgb head folded in
@@ -131,6 +133,7 @@ extern "C" int ctx_mlp_describe(int D, uint32_t skip_mask, int in_pts, int in_vi
     V.w_off = w_off; w_off += (V.n_h + V.n_x_post) * CTX_MLP_KC * V.N * 2;
     V.wt_off = wt_off; wt_off += (CTX_MLP_W / 2) * 256 * 2;
     V.act_slot = slot; slot += 128 * V.N * 2;
+    V.mask_slot = slot; slot += 128 * (V.N / 32) * 4;
     V.in_slot = prev_slot;
     ++n;
     net.head_off = f_off; f_off += 648;

@@ -39,6 +39,7 @@ _SIGNATURES = {
     "ctx_mlp_describe": (c_int, [c_int, ctypes.c_uint32, c_int, c_int, c_int, P]),
     "ctx_mlp_pack": (c_int, [P, P, c_int, P, P, P, P]),
     "ctx_mlp_fwd": (c_int, [P, P, P, c_int, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int64, P, P, P]),
+    "ctx_mlp_bwd": (c_int, [P, P, P, P, P, P, c_int64, P, c_int, P]),
     "ctx_tcgen05_selftest": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
 }
 

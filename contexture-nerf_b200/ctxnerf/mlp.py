@@ -96,7 +96,7 @@ class _MlpFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, x, rays, *params):
         desc: NetDesc = module._desc
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        need_grad = any(ctx.needs_input_grad[3:])
         w, wt, f = module._packed.get(list(params))
         if x is not None:
             if not x.is_cuda:

@@ -124,6 +124,15 @@ int ctx_mlp_fwd(const void* net, const void* wpacked, const float* fparams, int 
                 const float* z, int S, int L_pts, int L_dirs, int64_t P, float* out, void* acts,
                 void* stream);
 
+/* Backward of ctx_mlp_fwd w.r.t. the parameters (hand-written dgrad + wgrad
+ * tcgen05 kernels; the encoded inputs are data and get no gradient).  g_out
+ * [P,out_ch]; acts = records written by ctx_mlp_fwd; dacts = scratch of the same
+ * size; grads = HOST array of DEVICE pointers in the order of ctx_mlp_pack's
+ * params; gradients are ACCUMULATED (+=) into them.                              */
+int ctx_mlp_bwd(const void* net, const void* wtpacked, const float* fparams, const float* g_out,
+                const void* acts, void* dacts, int64_t P, float* const* grads, int n_grads,
+                void* stream);
+
 /* diagnostic: one-CTA tcgen05 GEMM C[128,N] = A * B^T (tests pin the descriptor
  * conventions with it); A,B bf16.  mode 0 K-major operands, 1 MN-major.          */
 int ctx_tcgen05_selftest(const void* A, const void* B, float* C, int N, int K, int mode, int variant,

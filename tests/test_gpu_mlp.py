@@ -123,3 +123,68 @@ def test_state_dict_roundtrip_with_reference_names(cuda):
     x = torch.rand(300, 42, device=cuda)
     with torch.no_grad():
         assert torch.equal(net.to(cuda)(x), net2.to(cuda)(x))
+
+
+@pytest.mark.parametrize("views,in_pts,out_ch,P", [(False, 63, 4, 3000), (False, 42, 3, 4096), (True, 63, 4, 2500)])
+def test_mlp_backward_matches_autograd_through_the_oracle(cuda, views, in_pts, out_ch, P):
+    """hand-written dgrad + wgrad kernels vs fp32 autograd of the reference forward.
+    Tolerance: 2e-2 of each gradient tensor's scale (bf16 operands)."""
+    net, params = _net(cuda, views, seed=7 + P, in_pts=in_pts, out_ch=out_ch)
+    g = torch.Generator().manual_seed(2)
+    v = 27 if views else 0
+    x = torch.randn(P, in_pts + v, generator=g).clamp(-1, 1)
+    gout = torch.randn(P, out_ch, generator=g) / P
+    # Reference gradient: autograd through the oracle's bf16-operand emulation of the same forward.
+    # (Against the pure-fp32 forward ~1% of the ReLU gates sit on the other side of zero, and with a
+    # random-sign g_out that alone moves each summed gradient by ~10%: not a kernel property.)
+    pr = {k: t.clone().requires_grad_(True) for k, t in params.items()}
+    orc.mlp_forward_bf16(pr, x, input_ch_views=v).backward(gout)
+    out = net(x.to(cuda))
+    out.backward(gout.to(cuda))
+    torch.cuda.synchronize()
+    worst_max, worst_l2 = 0.0, 0.0
+    for name, p in net.named_parameters():
+        ref = pr[name].grad
+        got = p.grad.cpu()
+        assert got.shape == ref.shape
+        emax = (got - ref).abs().max().item() / (ref.abs().max().item() + 1e-20)
+        el2 = (got - ref).norm().item() / (ref.norm().item() + 1e-20)
+        _diag(f"mlp bwd views={views} {name}: max-rel {emax:.3e} l2-rel {el2:.3e}")
+        worst_max, worst_l2 = max(worst_max, emax), max(worst_l2, el2)
+    # bf16 operands + the occasional ReLU gate on the other side of zero (different fp32 summation
+    # order than the emulation): 2e-2 in the L2 sense, 4e-2 for the single worst element
+    assert worst_l2 < 2e-2 and worst_max < 4e-2, (worst_l2, worst_max)
+
+
+def test_mlp_backward_fused_rays_training_step(cuda):
+    """render_rays coarse+fine -> img2mse loss -> backward, against the oracle's autograd."""
+    from ctxnerf import run_nerf_helpers as rh
+    coarse, pc = _net(cuda, True, seed=21)
+    fine, pf = _net(cuda, True, seed=22)
+    R, S, Ni = 192, 64, 128
+    g = torch.Generator().manual_seed(9)
+    o = torch.randn(R, 3, generator=g) * 0.05 + torch.tensor([0.0, 2.0, 3.5])
+    d = torch.randn(R, 3, generator=g)
+    vd = d / d.norm(dim=-1, keepdim=True)
+    rays = torch.cat([o, d, torch.full((R, 1), 2.0), torch.full((R, 1), 6.0), vd], -1)
+    tgt = torch.rand(R, 3, generator=g)
+    jit = torch.rand(R, S, generator=g)
+    out = rh.render_rays(rays.to(cuda), coarse, rh.FusedQuery(), S, N_importance=Ni, network_fine=fine,
+                         perturb=0.0, white_bkgd=True)
+    loss = rh.img2mse(out["rgb_map"], tgt.to(cuda)) + rh.img2mse(out["rgb0"], tgt.to(cuda))
+    loss.backward()
+    prc = {k: t.clone().requires_grad_(True) for k, t in pc.items()}
+    prf = {k: t.clone().requires_grad_(True) for k, t in pf.items()}
+    q = lambda pts, v, prm: orc.run_network(pts, v, prm, bf16_operands=True)
+    ref = orc.render_rays(rays, prc, q, S, N_importance=Ni, network_fine=prf, white_bkgd=True)
+    loss_ref = orc.img2mse(ref["rgb_map"], tgt) + orc.img2mse(ref["rgb0"], tgt)
+    loss_ref.backward()
+    _diag(f"train step: loss {loss.item():.6f} vs oracle {loss_ref.item():.6f}")
+    assert abs(loss.item() - loss_ref.item()) < 2e-2 * abs(loss_ref.item())
+    for tag, net, pr in (("coarse", coarse, prc), ("fine", fine, prf)):
+        worst = 0.0
+        for name, p in net.named_parameters():
+            refg = pr[name].grad
+            worst = max(worst, (p.grad.cpu() - refg).norm().item() / (refg.norm().item() + 1e-20))
+        _diag(f"train step {tag}: worst l2-rel grad err {worst:.3e}")
+        assert worst < 3e-2, (tag, worst)
