@@ -1,0 +1,264 @@
+#!/usr/bin/env python
+"""bench.py -- rays/s of the coarse(64)+fine(128) NeRF training step (fwd+bwd) on B200.
+
+    python bench.py --gpus N --steps K --warmup W           (N > 1: launched by torchrun)
+    python bench.py --impl reference ...                    (CPU arm: the oracle port on the host cores)
+
+Prints ONE JSON line (rank 0).  Workload = BASELINE.json configs[2]: 4096 rays per GPU
+drawn from the 800x800 config-2 camera, two view-direction D=8/W=256 MLPs, L=10/4
+encodings, stratified sampling (perturb=1), white background, MSE loss on rgb and rgb0,
+gradient all-reduce, Adam.  Synthetic rays/targets, random-init weights.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "contexture-nerf_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+RAYS_PER_GPU = 4096
+N_SAMPLES, N_IMPORTANCE = 64, 128
+MACS_PER_EVAL = 593408                       # view-direction net, SURVEY.md 8d
+EVALS_PER_RAY = N_SAMPLES + (N_SAMPLES + N_IMPORTANCE)
+METRIC = "rays/sec fwd+bwd (64+128 samples)"
+CONFIG = {"workload": "configs[2]: training step fwd+bwd, 4096-ray batch per GPU, coarse 64 + fine 128, "
+                      "D=8/W=256 view-dir MLPs, L=10/4, gradient all-reduce + Adam",
+          "rays_per_gpu": RAYS_PER_GPU, "n_samples": N_SAMPLES, "n_importance": N_IMPORTANCE,
+          "image": "800x800 config-2 camera", "perturb": 1.0, "white_bkgd": True,
+          "l2": "no explicit flush: each step streams ~10 GB of activation records through the 126 MB L2"}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": p["hbm_gbs"], "tf_burst": p["bf16_tflops"], "tf_sustained": p["bf16_tflops_sustained"],
+                "source": "measured"}
+    except Exception:
+        return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_step_sample(n_rays, threads, steps, warmup):
+    """The oracle port (oracle/nerf_oracle.py) doing the same training step on the host cores."""
+    from oracle import nerf_oracle as orc
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(0)
+    K, c2w = orc.lego_like_camera()
+    pc = {k: v.requires_grad_(True) for k, v in orc.init_mlp_params(63, 4, input_ch_views=27, generator=g).items()}
+    pf = {k: v.requires_grad_(True) for k, v in orc.init_mlp_params(63, 4, input_ch_views=27, generator=g).items()}
+    _, rd = orc.get_rays(800, 800, K, c2w)
+    rd = rd.reshape(-1, 3)
+    q = lambda pts, vd, prm: orc.run_network(pts, vd, prm)
+    times = []
+    for it in range(warmup + steps):
+        idx = torch.randint(0, 800 * 800, (n_rays,), generator=g)
+        d = rd[idx]
+        o = c2w[:3, -1].expand(n_rays, 3)
+        vd = d / d.norm(dim=-1, keepdim=True)
+        rays = torch.cat([o, d, torch.full((n_rays, 1), 2.0), torch.full((n_rays, 1), 6.0), vd], -1)
+        tgt = torch.rand(n_rays, 3, generator=g)
+        t0 = time.perf_counter()
+        out = orc.render_rays(rays, pc, q, N_SAMPLES, N_importance=N_IMPORTANCE, network_fine=pf, perturb=1.0,
+                              white_bkgd=True)
+        loss = orc.img2mse(out["rgb_map"], tgt) + orc.img2mse(out["rgb0"], tgt)
+        for p in list(pc.values()) + list(pf.values()):
+            p.grad = None
+        loss.backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return times
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_rays = 256
+    times = cpu_step_sample(n_rays, threads, args.steps, min(args.warmup, 2))
+    total = sum(times)
+    val = n_rays * len(times) / total
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "rays/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(CONFIG, sample=f"{n_rays} rays per step (bounded sample of the 4096-ray batch)"),
+            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": "port",
+                             "sample": f"{n_rays}-ray coarse+fine fwd+bwd step, oracle/nerf_oracle.py (torch CPU fp32), "
+                                       f"{len(times)} steps"},
+            "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    from ctxnerf import _lib
+    from ctxnerf.train import NerfTrainer
+    from ctxnerf.workloads import orbit_camera
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: ctxnerf has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    warm = max(args.warmup, 3)
+    K, c2w = orbit_camera()
+    tr = NerfTrainer(800, 800, K, c2w, near=2.0, far=6.0, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE,
+                     perturb=1.0, white_bkgd=True, device=dev, seed=0)
+    # per-rank synthetic batches (seed 0 + rank), resident on the device and mirrored in pinned host memory
+    g = torch.Generator().manual_seed(0 + rank)
+    NB = 8
+    idx_h = [torch.randint(0, 800 * 800, (RAYS_PER_GPU,), generator=g).pin_memory() for _ in range(NB)]
+    tgt_h = [torch.rand(RAYS_PER_GPU, 3, generator=g).pin_memory() for _ in range(NB)]
+    idx_d = [t.to(dev) for t in idx_h]
+    tgt_d = [t.to(dev) for t in tgt_h]
+    loss_h = torch.zeros(1).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def timed(step_fn, steps, with_timers):
+        for i in range(warm):
+            step_fn(i)
+        torch.cuda.synchronize()
+        barrier()
+        tr.timers = {} if with_timers else None
+        l0 = _lib.launch_count
+        cs = ClockSampler(local)
+        cs.start()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for i in range(steps):
+            step_fn(warm + i)
+        b.record()
+        torch.cuda.synchronize()
+        clocks = cs.stop()
+        barrier()
+        ms = a.elapsed_time(b)
+        launches = _lib.launch_count - l0
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        timers, tr.timers = tr.timers, None
+        return t.item(), clocks, launches, timers
+
+    # ---- device-resident inputs ("value") ----
+    ms, clocks, launches, timers = timed(lambda i: tr.step(idx_d[i % NB], tgt_d[i % NB]), args.steps, True)
+    value = RAYS_PER_GPU * world * args.steps / (ms * 1e-3)
+    # ---- end to end through the public API with host buffers ----
+    ms_e2e, _, _, _ = timed(lambda i: (tr.step_from_host(idx_h[i % NB], tgt_h[i % NB], loss_h), torch.cuda.current_stream().synchronize()),
+                            args.steps, False)
+    e2e = RAYS_PER_GPU * world * args.steps / (ms_e2e * 1e-3)
+    final_loss = float(loss_h.item())
+
+    # ---- per-kernel device times inside the timed region -> roofline of the dominant kernel ----
+    pk = peaks()
+    kern = {}
+    for name, evs in (timers or {}).items():
+        kern[name] = sum(x.elapsed_time(y) for x, y in evs) / len(evs)
+    flops = {"mlp_fwd_coarse": 2.0 * MACS_PER_EVAL * RAYS_PER_GPU * N_SAMPLES,
+             "mlp_fwd_fine": 2.0 * MACS_PER_EVAL * RAYS_PER_GPU * (N_SAMPLES + N_IMPORTANCE)}
+    flops["mlp_bwd_coarse"] = 2 * flops["mlp_fwd_coarse"]
+    flops["mlp_bwd_fine"] = 2 * flops["mlp_fwd_fine"]
+    dom = max(kern, key=kern.get) if kern else None
+    roofline = None
+    if dom:
+        ach = flops[dom] / (kern[dom] * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"] + " (sustained)",
+                    "ms_per_launch": kern[dom]}
+    step_flops = 3 * 2.0 * MACS_PER_EVAL * RAYS_PER_GPU * EVALS_PER_RAY
+    line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": CONFIG, "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": RAYS_PER_GPU * (8 + 12),
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "roofline": roofline,
+            "step_tensor_frac": step_flops / (ms / args.steps * 1e-3) / 1e12 / pk["tf_sustained"],
+            "kernel_ms": kern, "final_loss": final_loss}
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            n = 256
+            times = cpu_step_sample(n, threads, 3, 1)
+            line["cpu_baseline"] = {"value": n * len(times) / sum(times), "unit": "rays/s", "cores": threads,
+                                    "kind": "port",
+                                    "sample": f"{n}-ray coarse+fine fwd+bwd step x{len(times)}, oracle/nerf_oracle.py "
+                                              "(torch CPU fp32, all host threads)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

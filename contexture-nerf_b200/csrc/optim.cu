@@ -1,0 +1,73 @@
+// Fused Adam over the flat parameter / gradient buckets of the two NeRF MLPs
+// (the reference trains with torch.optim.Adam, src/training/trainer.py:603),
+// and the fused photometric loss: img2mse(rgb, t) + img2mse(rgb0, t)
+// (src/run_nerf_helpers.py:9) with its gradient in one pass.
+#include "ctx_common.cuh"
+
+namespace ctx {
+
+// torch.optim.Adam semantics (no amsgrad, optional L2 weight decay), bias-corrected.
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                            float bc1, float bc2_sqrt, float wd, float grad_scale) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * grad_scale;
+    if (wd != 0.f) gi += wd * p[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
+// loss = mean((a-t)^2) [+ mean((b-t)^2)]; g_a = 2(a-t)/n * scale, g_b likewise.  One CTA.
+__global__ void mse_pair_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                const float* __restrict__ t, int64_t n, float scale, float* __restrict__ loss,
+                                float* __restrict__ g_a, float* __restrict__ g_b) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  const float inv = 1.0f / (float)n;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const float ti = t[i];
+    const float da = a[i] - ti;
+    acc += da * da;
+    if (g_a) g_a[i] = 2.f * da * inv * scale;
+    if (b) {
+      const float db = b[i] - ti;
+      acc += db * db;
+      if (g_b) g_b[i] = 2.f * db * inv * scale;
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) loss[0] = v * inv;
+  }
+}
+
+}  // namespace ctx
+
+extern "C" int ctx_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                             float lr, float beta1, float beta2, float eps, int step, float weight_decay,
+                             float grad_scale, void* stream) {
+  if (n < 0 || step < 1 || !params || !grads || !exp_avg || !exp_avg_sq) return CTX_ERR_BAD_ARG;
+  if (n == 0) return 0;
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2 = sqrtf(1.f - powf(beta2, (float)step));
+  int64_t blocks = ctx::ceil_div(n, 256);
+  if (blocks > ctx::kNumSMs * 8) blocks = ctx::kNumSMs * 8;
+  ctx::adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1,
+                                                                  beta2, eps, bc1, bc2, weight_decay, grad_scale);
+  CTX_RETURN_LAST();
+}
+
+extern "C" int ctx_mse_fwd_bwd(const float* a, const float* b, const float* target, int64_t n, float scale,
+                               float* loss, float* g_a, float* g_b, void* stream) {
+  if (n < 1 || !a || !target || !loss) return CTX_ERR_BAD_ARG;
+  ctx::mse_pair_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(a, b, target, n, scale, loss, g_a, g_b);
+  CTX_RETURN_LAST();
+}

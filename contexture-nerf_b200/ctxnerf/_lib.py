@@ -40,6 +40,8 @@ _SIGNATURES = {
     "ctx_mlp_pack": (c_int, [P, P, c_int, P, P, P, P]),
     "ctx_mlp_fwd": (c_int, [P, P, P, c_int, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int64, P, P, P]),
     "ctx_mlp_bwd": (c_int, [P, P, P, P, P, P, c_int64, P, c_int, P]),
+    "ctx_adam_step": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_int, c_float, c_float, P]),
+    "ctx_mse_fwd_bwd": (c_int, [P, P, P, c_int64, c_float, P, P, P, P]),
     "ctx_tcgen05_selftest": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
 }
 
@@ -76,7 +78,14 @@ def check(code: int, what: str) -> None:
         raise CtxNerfError(f"{what} failed with code {code}: {msg.decode() if msg else '?'}")
 
 
+# kernels launched per ABI call (bench.py reports the total as gpu_launches)
+KERNELS_PER_CALL = {"ctx_mlp_bwd": 2}
+launch_count = 0
+
+
 def call(name: str, *args) -> None:
+    global launch_count
+    launch_count += KERNELS_PER_CALL.get(name, 1)
     fn = getattr(lib(), name, None)
     if fn is None:
         raise CtxNerfError(f"libctxnerf.so does not export {name}; rebuild the extension")

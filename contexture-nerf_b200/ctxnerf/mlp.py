@@ -52,6 +52,11 @@ class PackedWeights:
         self.desc = desc
         self._per_dev = {}
 
+    def invalidate(self):
+        """Force a re-pack (parameters were updated in place by a non-torch kernel)."""
+        for dev in list(self._per_dev):
+            self._per_dev[dev] = (None, self._per_dev[dev][1])
+
     def get(self, params: List[torch.Tensor]):
         dev = params[0].device
         key = tuple((p.data_ptr(), p._version) for p in params)
@@ -89,41 +94,41 @@ def _launch_fwd(desc: NetDesc, w, f, *, x=None, rays=None, P: int, out, acts=Non
                  L_pts, L_dirs, P, ptr(out), ptr(acts), stream_ptr(dev))
 
 
+def forward_raw(module, *, x=None, rays=None, save_acts=False):
+    """Launch the fused forward.  Returns (out [P,out_ch], acts or None, P, packed)."""
+    module._ensure()
+    desc: NetDesc = module._desc
+    packed = module._packed.get(module._param_list())
+    w, wt, f = packed
+    if x is not None:
+        if not x.is_cuda:
+            raise _lib.CtxNerfError("ctxnerf MLP runs on CUDA tensors only (no CPU fallback)")
+        x = x.reshape(-1, x.shape[-1]).float().contiguous()
+        P, dev = x.shape[0], x.device
+    else:
+        z = rays[3]
+        P, dev = z.numel(), z.device
+    out = torch.empty(P, desc.out_ch, device=dev, dtype=torch.float32)
+    acts = None
+    if save_acts:
+        ntiles = (P + TILE - 1) // TILE
+        ntiles += ntiles & 1
+        acts = torch.empty(ntiles * desc.act_tile_bytes, dtype=torch.uint8, device=dev)
+    _launch_fwd(desc, w, f, x=x, rays=rays, P=P, out=out, acts=acts, L_pts=module.L_pts, L_dirs=module.L_dirs)
+    return out, acts, P, packed
+
+
 class _MlpFn(torch.autograd.Function):
     """out = MLP(x or rays).  Gradients flow to the parameters only (inputs are
     data: encodings of fixed coordinates)."""
 
     @staticmethod
     def forward(ctx, module, x, rays, *params):
-        desc: NetDesc = module._desc
         need_grad = any(ctx.needs_input_grad[3:])
-        w, wt, f = module._packed.get(list(params))
-        if x is not None:
-            if not x.is_cuda:
-                raise _lib.CtxNerfError("ctxnerf MLP runs on CUDA tensors only (no CPU fallback)")
-            lead = x.shape[:-1]
-            x2 = x.reshape(-1, x.shape[-1]).float().contiguous()
-            P = x2.shape[0]
-            dev = x.device
-        else:
-            o, d, v, z = rays
-            lead = z.shape
-            P = z.numel()
-            x2 = None
-            dev = z.device
-        out = torch.empty(P, desc.out_ch, device=dev, dtype=torch.float32)
-        acts = None
-        if need_grad:
-            ntiles = (P + TILE - 1) // TILE
-            ntiles += ntiles & 1
-            acts = torch.empty(ntiles * desc.act_tile_bytes, dtype=torch.uint8, device=dev)
-        _launch_fwd(desc, w, f, x=x2, rays=rays, P=P, out=out, acts=acts, L_pts=module.L_pts, L_dirs=module.L_dirs)
-        ctx.module = module
-        ctx.P = P
-        ctx.acts = acts
-        ctx.packed = (w, wt, f)
-        ctx.n_params = len(params)
-        return out.reshape(*lead, desc.out_ch)
+        lead = x.shape[:-1] if x is not None else rays[3].shape
+        out, acts, P, packed = forward_raw(module, x=x, rays=rays, save_acts=need_grad)
+        ctx.module, ctx.P, ctx.acts, ctx.packed = module, P, acts, packed
+        return out.reshape(*lead, module._desc.out_ch)
 
     @staticmethod
     def backward(ctx, g_out):

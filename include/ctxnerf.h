@@ -133,6 +133,19 @@ int ctx_mlp_bwd(const void* net, const void* wtpacked, const float* fparams, con
                 const void* acts, void* dacts, int64_t P, float* const* grads, int n_grads,
                 void* stream);
 
+/* ---- training-step glue ------------------------------------------------------
+ * img2mse(a,t) + img2mse(b,t) (src/run_nerf_helpers.py:9) and its gradient in one
+ * pass: loss[0] = mean((a-t)^2) [+ mean((b-t)^2)], g_a = 2(a-t)/n*scale (b, g_*
+ * nullable).  n = number of elements.                                            */
+int ctx_mse_fwd_bwd(const float* a, const float* b, const float* target, int64_t n, float scale,
+                    float* loss, float* g_a, float* g_b, void* stream);
+/* torch.optim.Adam update (src/training/trainer.py:603) over flat fp32 buckets;
+ * step >= 1 is the bias-correction step, grad_scale multiplies the gradient
+ * (1/world_size after a sum all-reduce).                                         */
+int ctx_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                  float lr, float beta1, float beta2, float eps, int step, float weight_decay,
+                  float grad_scale, void* stream);
+
 /* diagnostic: one-CTA tcgen05 GEMM C[128,N] = A * B^T (tests pin the descriptor
  * conventions with it); A,B bf16.  mode 0 K-major operands, 1 MN-major.          */
 int ctx_tcgen05_selftest(const void* A, const void* B, float* C, int N, int K, int mode, int variant,
