@@ -121,10 +121,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_dgrad_kernel(const __grid_
     const int q = warp & 3;
     const int row = q * 32 + lane;
     uint8_t* my_h = h_buf + t * kHBytes;
-    uint8_t* my_x = x_buf + t * kXBytes;
     const uint32_t my_acc = tmem + t * CTX_MLP_W + ((uint32_t)(q * 32) << 16);
-    const int bar_id = 1 + t;
-    const bool tile_leader = (q == 2 && lane == 0);
     const float* hw = a.fparams + net.head_off;
     const bool has_views = net.in_views > 0;
     uint32_t acc_phase = 0;
@@ -151,8 +148,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_dgrad_kernel(const __grid_
         float gv[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) gv[i] = i < 4 ? g[i] : 0.f;
-        store_row8(my_x, row, 0, gv, false);
-        store_row8(my_x, row, 8, gv + 8, false);
+        store_row8(nullptr, row, 0, gv, false, drec + net.gout_slot);
+        store_row8(nullptr, row, 8, gv + 8, false, drec + net.gout_slot);
       }
       {
         const int nw = Last.N / 32;
@@ -178,17 +175,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_dgrad_kernel(const __grid_
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = mask_apply(v[j], neg, j);
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) store_row8(my_h, row, cb * 32 + j, v + j, false);
+          for (int j = 0; j < 32; j += 8) store_row8(my_h, row, cb * 32 + j, v + j, false, drec + Last.act_slot);
         }
       }
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&ctl->act_ready[t]);
-      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(kEpiThreadsPerTile));
-      if (tile_leader) {
-        tc::bulk_s2g(drec + Last.act_slot, my_h, (uint32_t)kTileM * Last.N * 2);
-        tc::bulk_s2g(drec + net.gout_slot, my_x, kTileM * 16 * 2);
-        tc::bulk_commit();
-      }
 
       for (int si = 0; si < a.n_steps; ++si) {
         const CtxMlpLayer& Dst = net.L[a.step_dst[si]];
@@ -206,8 +197,6 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_dgrad_kernel(const __grid_
         tc::mbar_wait(&ctl->acc_full[t], acc_phase);
         acc_phase ^= 1;
         tc::tc_fence_after();
-        if (tile_leader) tc::bulk_wait_read<0>();
-        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(kEpiThreadsPerTile));
         const bool add_alpha = (Dst.epi == CTX_EPI_HIDDEN_ALPHA);
 #pragma unroll
         for (int cb = 0; cb < 8; ++cb) {
@@ -222,21 +211,14 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_dgrad_kernel(const __grid_
             v[j] = mask_apply(x, mw[cb], j);
           }
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) store_row8(my_h, row, cb * 32 + j, v + j, false);
+          for (int j = 0; j < 32; j += 8)
+            store_row8(si + 1 < a.n_steps ? my_h : nullptr, row, cb * 32 + j, v + j, false, drec + Dst.act_slot);
         }
         tc::fence_proxy_async_smem();
         tc::tc_fence_before();
         if (si + 1 < a.n_steps) tc::mbar_arrive(&ctl->act_ready[t]);
-        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(kEpiThreadsPerTile));
-        if (tile_leader) {
-          tc::bulk_s2g(drec + Dst.act_slot, my_h, kHBytes);
-          tc::bulk_commit();
-        }
       }
-      if (tile_leader) tc::bulk_wait_read<0>();
-      asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(kEpiThreadsPerTile));
     }
-    if (tile_leader) tc::bulk_wait<0>();
   }
   tc::tc_fence_before();
   __syncthreads();

@@ -62,8 +62,11 @@ __device__ __forceinline__ void fast_sincos(float a, float& s, float& c) {
   c = __cosf(r);
 }
 
-// write 8 consecutive channels [ch0, ch0+8) of row `row` of a K-major A tile
-__device__ __forceinline__ void store_row8(uint8_t* tile, int row, int ch0, const float* v, bool relu) {
+// write 8 consecutive channels [ch0, ch0+8) of row `row` of a K-major A tile; `gtile` (nullable) is the
+// same tile image in HBM (activation / dZ record): the 16-byte row chunk is mirrored there straight from
+// registers (a warp covers 512 contiguous bytes), so saving activations needs no extra pass over shared memory
+__device__ __forceinline__ void store_row8(uint8_t* tile, int row, int ch0, const float* v, bool relu,
+                                           uint8_t* gtile = nullptr) {
   uint4 q;
   if (relu) {
     q.x = pack_bf16x2_relu(v[0], v[1]); q.y = pack_bf16x2_relu(v[2], v[3]);
@@ -72,8 +75,9 @@ __device__ __forceinline__ void store_row8(uint8_t* tile, int row, int ch0, cons
     q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
     q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
   }
-  *reinterpret_cast<uint4*>(tile + (ch0 >> 3) * kK8Stride + (row >> 3) * 128 + (row & 7) * 16) = q;
+  const uint32_t off = (ch0 >> 3) * kK8Stride + (row >> 3) * 128 + (row & 7) * 16;
+  if (tile) *reinterpret_cast<uint4*>(tile + off) = q;
+  if (gtile) *reinterpret_cast<uint4*>(gtile + off) = q;
 }
-
 
 }  // namespace ctx

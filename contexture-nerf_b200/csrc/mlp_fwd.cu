@@ -24,7 +24,8 @@ namespace ctx {
 
 // encode d-dim coordinate vector into channels [x | sin f0 x | cos f0 x | ...] padded with zeros to `pad`
 template <int PAD, int MAXL>
-__device__ __forceinline__ void encode_row(uint8_t* tile, int row, const float* xyz, int L, bool valid) {
+__device__ __forceinline__ void encode_row(uint8_t* tile, int row, const float* xyz, int L, bool valid,
+                                           uint8_t* gtile) {
   constexpr int d = 3;
   float v[PAD];
 #pragma unroll
@@ -50,7 +51,7 @@ __device__ __forceinline__ void encode_row(uint8_t* tile, int row, const float* 
     }
   }
 #pragma unroll
-  for (int c0 = 0; c0 < PAD; c0 += 8) store_row8(tile, row, c0, v + c0, false);
+  for (int c0 = 0; c0 < PAD; c0 += 8) store_row8(tile, row, c0, v + c0, false, gtile);
 }
 
 __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
@@ -148,8 +149,6 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fwd_kernel(const __grid_co
     uint8_t* my_h = h_buf + t * kHBytes;
     uint8_t* my_x = x_buf + t * kXBytes;
     const uint32_t my_acc = tmem + t * CTX_MLP_W + ((uint32_t)(q * 32) << 16);
-    const int bar_id = 1 + t;                 // named barrier of this tile's 128 threads
-    const bool tile_leader = (q == 2 && lane == 0);  // warps 2 and 6 are the first warps of their tile
     const float* fp = a.fparams;
     uint32_t acc_phase = 0;
     const bool has_views = net.in_views > 0;
@@ -172,21 +171,18 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fwd_kernel(const __grid_co
             if (has_views) dirs[j] = a.viewdirs[r * 3 + j];
           }
         }
-        encode_row<CTX_MLP_XP_PAD, 10>(my_x, row, xyz, a.L_pts, valid);
+        encode_row<CTX_MLP_XP_PAD, 10>(my_x, row, xyz, a.L_pts, valid, rec ? rec + net.xp_slot : nullptr);
       } else {
         float v[CTX_MLP_XP_PAD];
 #pragma unroll
         for (int i = 0; i < CTX_MLP_XP_PAD; ++i)
           v[i] = (valid && i < net.in_pts) ? __ldg(a.x + p * a.x_ld + i) : 0.f;
 #pragma unroll
-        for (int c0 = 0; c0 < CTX_MLP_XP_PAD; c0 += 8) store_row8(my_x, row, c0, v + c0, false);
+        for (int c0 = 0; c0 < CTX_MLP_XP_PAD; c0 += 8)
+          store_row8(my_x, row, c0, v + c0, false, rec ? rec + net.xp_slot : nullptr);
       }
       tc::fence_proxy_async_smem();
       tc::mbar_arrive(&ctl->act_ready[t]);
-      if (rec) {
-        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(kEpiThreadsPerTile));
-        if (tile_leader) { tc::bulk_s2g(rec + net.xp_slot, my_x, kXBytes); tc::bulk_commit(); }
-      }
 
       float alpha = 0.f;
       for (int l = 0; l < net.n_layers; ++l) {
@@ -194,11 +190,6 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fwd_kernel(const __grid_co
         tc::mbar_wait(&ctl->acc_full[t], acc_phase);
         acc_phase ^= 1;
         tc::tc_fence_after();
-        if (rec) {
-          // the previous bulk store must have finished READING my_h / my_x before they are rewritten
-          if (tile_leader) tc::bulk_wait_read<0>();
-          asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(kEpiThreadsPerTile));
-        }
         const bool is_final = (L.epi == CTX_EPI_FINAL_VIEWS || L.epi == CTX_EPI_FINAL_OUT);
         const bool write_h = !is_final || rec != nullptr;
         float head[4] = {0.f, 0.f, 0.f, 0.f};
@@ -246,21 +237,23 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fwd_kernel(const __grid_co
           }
           if (write_h) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) store_row8(my_h, row, cb * 32 + j, v + j, false);
+            for (int j = 0; j < 32; j += 8)
+              store_row8(is_final ? nullptr : my_h, row, cb * 32 + j, v + j, false, rec ? rec + L.act_slot : nullptr);
           }
         }
         if (L.epi == CTX_EPI_HIDDEN_ALPHA) {
           alpha += __ldg(hw + 256);
           // the point encoding is dead from here on: encode the view direction into the x buffer
           if (a.mode == 1) {
-            encode_row<CTX_MLP_XD_PAD, 4>(my_x, row, dirs, a.L_dirs, valid);
+            encode_row<CTX_MLP_XD_PAD, 4>(my_x, row, dirs, a.L_dirs, valid, rec ? rec + net.xd_slot : nullptr);
           } else {
             float vv[CTX_MLP_XD_PAD];
 #pragma unroll
             for (int i = 0; i < CTX_MLP_XD_PAD; ++i)
               vv[i] = (valid && i < net.in_views) ? __ldg(a.x + p * a.x_ld + net.in_pts + i) : 0.f;
 #pragma unroll
-            for (int c0 = 0; c0 < CTX_MLP_XD_PAD; c0 += 8) store_row8(my_x, row, c0, vv + c0, false);
+            for (int c0 = 0; c0 < CTX_MLP_XD_PAD; c0 += 8)
+              store_row8(my_x, row, c0, vv + c0, false, rec ? rec + net.xd_slot : nullptr);
           }
         }
         if (is_final) {
@@ -271,31 +264,17 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_fwd_kernel(const __grid_co
               *reinterpret_cast<float4*>(a.out + p * 4) = o4;
             } else {
               const float* bo = hw + 1024;
-              for (int o = 0; o < net.out_ch; ++o) a.out[p * net.out_ch + o] = head[o] + __ldg(bo + o);
+#pragma unroll
+              for (int o = 0; o < 4; ++o)
+                if (o < net.out_ch) a.out[p * net.out_ch + o] = head[o] + __ldg(bo + o);
             }
           }
         }
-        if (!is_final || rec) {
-          tc::fence_proxy_async_smem();
-        }
+        if (!is_final) tc::fence_proxy_async_smem();
         tc::tc_fence_before();
         if (!is_final) tc::mbar_arrive(&ctl->act_ready[t]);
-        if (rec) {
-          asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(kEpiThreadsPerTile));
-          if (tile_leader) {
-            tc::bulk_s2g(rec + L.act_slot, my_h, (uint32_t)kTileM * L.N * 2);
-            if (L.epi == CTX_EPI_HIDDEN_ALPHA) tc::bulk_s2g(rec + net.xd_slot, my_x, kTileM * CTX_MLP_XD_PAD * 2);
-            tc::bulk_commit();
-          }
-        }
-      }
-      if (rec) {
-        // buffers are rewritten by the next iteration's encode
-        if (tile_leader) tc::bulk_wait_read<0>();
-        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(kEpiThreadsPerTile));
       }
     }
-    if (a.acts && tile_leader) tc::bulk_wait<0>();
   }
 
   tc::tc_fence_before();

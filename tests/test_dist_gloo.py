@@ -1,0 +1,110 @@
+"""Host-side multi-GPU logic on CPU: world_size-2 gloo.  Ray sharding, per-rank
+RNG streams, the flat gradient bucket and its single all-reduce (the only
+collective of the path)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import PKG, ROOT
+
+
+def _worker(rank, world, port, q):
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ctxnerf.dist import FlatBucket, rank_generator, shard_rays, world as world_fn
+        assert world_fn() == (rank, world)
+        torch.manual_seed(0)                      # identical initial weights on every rank
+        nets = [torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3)) for _ in range(2)]
+        before = [p.detach().clone() for n in nets for p in n.parameters()]
+        bucket = FlatBucket(nets)
+        # parameters became views of one flat tensor, values preserved, grads are views of one bucket
+        off = 0
+        for p, b in zip(bucket.params, before):
+            assert torch.equal(p.detach(), b)
+            assert p.data_ptr() == bucket.flat.data_ptr() + 4 * off
+            assert p.grad.data_ptr() == bucket.grad.data_ptr() + 4 * off
+            off += p.numel()
+        assert off == bucket.numel
+        # this rank's shard of a global batch of 10 rays
+        g = torch.Generator().manual_seed(123)
+        x_all, y_all = torch.randn(10, 5, generator=g), torch.randn(10, 3, generator=g)
+        lo, hi = shard_rays(10, rank, world)
+        bucket.zero_grad()
+        loss = sum(((n(x_all[lo:hi]) - y_all[lo:hi]) ** 2).sum() for n in nets)
+        loss.backward()                            # autograd accumulates in place into the bucket views
+        assert bucket.params[0].grad.data_ptr() == bucket.grad.data_ptr()
+        bucket.all_reduce()
+        # reference: single-process gradient of the concatenated batch
+        torch.manual_seed(0)
+        ref = [torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.ReLU(), torch.nn.Linear(7, 3)) for _ in range(2)]
+        sum(((n(x_all) - y_all) ** 2).sum() for n in ref).backward()
+        flat_ref = torch.cat([p.grad.reshape(-1) for n in ref for p in n.parameters()])
+        torch.testing.assert_close(bucket.grad, flat_ref, rtol=1e-5, atol=1e-6)
+        # per-rank RNG streams differ, are reproducible
+        a = torch.randint(0, 640000, (8,), generator=rank_generator(0, rank))
+        b = torch.randint(0, 640000, (8,), generator=rank_generator(0, rank))
+        assert torch.equal(a, b)
+        gathered = [torch.zeros_like(a) for _ in range(world)]
+        dist.all_gather(gathered, a)
+        assert not torch.equal(gathered[0], gathered[1])
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        q.put((rank, repr(e)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
+def test_shard_rays_covers_everything():
+    from ctxnerf.dist import shard_rays
+    for n, w in ((640000, 8), (10, 3), (7, 8), (0, 2)):
+        spans = [shard_rays(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        sizes = [b - a for a, b in spans]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_reference_arm_of_bench_runs_on_cpu():
+    """bench.py --impl reference (the oracle port on the host cores) prints the contract's JSON line."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "rays/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_product_fails_loudly_without_cuda():
+    """No CPU fallback: calling an op on CPU tensors raises instead of silently computing."""
+    from ctxnerf import _lib, ops
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(_lib.CtxNerfError):
+        ops.composite(torch.zeros(2, 4, 4), torch.zeros(2, 4), torch.zeros(2, 3))
+    from ctxnerf import run_nerf_helpers as rh
+    with pytest.raises(_lib.CtxNerfError):
+        rh.sample_pdf(torch.zeros(2, 5), torch.zeros(2, 4), 8, det=True)
