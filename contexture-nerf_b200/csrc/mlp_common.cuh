@@ -31,6 +31,8 @@ struct MlpFwdArgs {
   int64_t P;
   float* out;               // [P, out_ch]
   uint8_t* acts;            // nullable: per-tile activation records (training)
+  unsigned long long* prof; // nullable: per-CTA cycle counters (diagnostics), 16 per CTA
+  int debug;                // diagnostics: 1 = epilogue skips TMEM loads/stores, 2 = issuer skips the MMAs
 };
 
 struct __align__(8) MlpSmemCtl {

@@ -37,6 +37,10 @@ typedef struct {
   int32_t act_slot;  /* byte offset, within a tile's activation record, of this layer's OUTPUT */
   int32_t in_slot;   /* byte offset of the record holding this layer's h INPUT (-1: none) */
   int32_t mask_slot; /* byte offset of the ReLU sign-bit record (128 rows x N/32 words), -1: none */
+  int32_t bias_mma;  /* 2-CTA kernels fold the bias into the GEMM through the constant-1 pad channel of the x
+                        buffer: 0 = it rides in an x chunk this layer reads anyway, 1 = one extra K=16 MMA whose
+                        B operand is the 16-wide "bias chunk" stored after the layer's regular chunks */
+  int32_t bias_a_off;/* byte offset inside the x tile of the 16 channels ending in the constant-1 channel */
 } CtxMlpLayer;
 
 typedef struct {

@@ -306,7 +306,7 @@ extern "C" int ctx_mlp_fwd(const void* net_host, const void* wpacked, const floa
   }
   a.wpacked = (const uint8_t*)wpacked; a.fparams = fparams; a.mode = mode; a.x = x; a.x_ld = x_ld;
   a.rays_o = rays_o; a.rays_d = rays_d; a.viewdirs = viewdirs; a.z = z; a.S = S; a.L_pts = L_pts;
-  a.L_dirs = L_dirs; a.P = P; a.out = out; a.acts = (uint8_t*)acts;
+  a.L_dirs = L_dirs; a.P = P; a.out = out; a.acts = (uint8_t*)acts; a.prof = nullptr; a.debug = 0;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(ctx::mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -22,12 +22,14 @@ struct PackLayer {
   int nseg; PackSeg seg[3];
   int w_off, wt_off, bias_off;
   int h_src;               // source column of the h part (transposed stream), -1: none
+  int bias_mma;            // split copy: extra 16-wide bias chunk after the regular chunks
   int Kt;                  // K extent (= out features padded to 32) of the transposed stream
 };
 struct PackArgs {
   int n_layers;
   PackLayer L[CTX_MLP_MAX_LAYERS];
   uint16_t* w; uint16_t* wt; float* fparams;
+  int w_bytes, wt_bytes;   // each stream buffer holds two copies: [0,bytes) whole-N chunks, [bytes,2*bytes) half-split
   // heads
   int has_views, out_ch, head_off;
   const float* w_alpha; const float* b_alpha; const float* w_rgb; const float* b_rgb;
@@ -63,13 +65,33 @@ __global__ void mlp_pack_kernel(const __grid_constant__ PackArgs a) {
     const int k8 = r0 / (L.N * 8), r1 = r0 - k8 * (L.N * 8);
     const int n = r1 >> 3, kk = r1 & 7;
     int k = c * 32 + k8 * 8 + kk, col = -1;
+    bool one_channel = false;   // last padded channel of an x segment: constant 1 in the 2-CTA kernels
     for (int s = 0; s < L.nseg; ++s) {
-      if (k < L.seg[s].pad) { if (k < L.seg[s].len) col = L.seg[s].src + k; break; }
+      if (k < L.seg[s].pad) {
+        if (k < L.seg[s].len) col = L.seg[s].src + k;
+        else if (k == L.seg[s].pad - 1) one_channel = true;
+        break;
+      }
       k -= L.seg[s].pad;
     }
-    dst[e] = (col >= 0 && n < L.out_rows) ? f2bf(L.W[(size_t)n * L.ld + col]) : (uint16_t)0;
+    uint16_t val = (col >= 0 && n < L.out_rows) ? f2bf(L.W[(size_t)n * L.ld + col]) : (uint16_t)0;
+    dst[e] = val;
+    if (one_channel && !L.bias_mma && n < L.out_rows) val = f2bf(L.b[n]);   // bias rides on the constant-1 channel
+    // half-split copy for the 2-CTA kernels: chunk = [half][k8][N/2][8]
+    const int Nh = L.N >> 1, hf = n / Nh, nl = n - hf * Nh;
+    a.w[(a.w_bytes + L.w_off) / 2 + c * (L.N * 32) + hf * (Nh * 32) + k8 * (Nh * 8) + nl * 8 + kk] = val;
   }
   for (int i = tid; i < L.N; i += nth) a.fparams[L.bias_off + i] = i < L.out_rows ? L.b[i] : 0.f;
+  if (L.bias_mma) {   // [half][2 k8][N/2][8]: bias at k = 15 (the constant-1 channel), zeros elsewhere
+    uint16_t* bc = a.w + (a.w_bytes + L.w_off) / 2 + Kpad * L.N;
+    const int Nh = L.N >> 1;
+    for (int e = tid; e < 16 * L.N; e += nth) {
+      const int hf = e / (16 * Nh), r0 = e - hf * 16 * Nh;
+      const int k8 = r0 / (Nh * 8), r1 = r0 - k8 * Nh * 8;
+      const int nl = r1 >> 3, kk = r1 & 7, n = hf * Nh + nl;
+      bc[e] = (k8 == 1 && kk == 7 && n < L.out_rows) ? f2bf(L.b[n]) : (uint16_t)0;
+    }
+  }
   // transposed stream (dgrad): B_T[n' = h input feature (256)][k = output feature], chunks over k
   if (L.wt_off >= 0 && a.wt != nullptr) {
     uint16_t* dt = a.wt + L.wt_off / 2;
@@ -79,7 +101,10 @@ __global__ void mlp_pack_kernel(const __grid_constant__ PackArgs a) {
       const int k8 = r0 / (256 * 8), r1 = r0 - k8 * (256 * 8);
       const int n = r1 >> 3, kk = r1 & 7;
       const int k = c * 32 + k8 * 8 + kk;  // output feature
-      dt[e] = (k < L.out_rows) ? f2bf(L.W[(size_t)k * L.ld + L.h_src + n]) : (uint16_t)0;
+      const uint16_t val = (k < L.out_rows) ? f2bf(L.W[(size_t)k * L.ld + L.h_src + n]) : (uint16_t)0;
+      dt[e] = val;
+      const int hf = n >> 7, nl = n & 127;
+      a.wt[(a.wt_bytes + L.wt_off) / 2 + c * (256 * 32) + hf * (128 * 32) + k8 * (128 * 8) + nl * 8 + kk] = val;
     }
   }
 }
@@ -110,6 +135,8 @@ extern "C" int ctx_mlp_describe(int D, uint32_t skip_mask, int in_pts, int in_vi
     L.n_x_post = 0; L.N = CTX_MLP_W; L.relu = 1; L.epi = CTX_EPI_HIDDEN;
     L.bias_off = f_off; f_off += L.N;
     L.w_off = w_off; w_off += (L.n_x_pre + L.n_h) * CTX_MLP_KC * L.N * 2;
+    L.bias_mma = L.n_x_pre ? 0 : 1; L.bias_a_off = (CTX_MLP_XP_PAD - 16) / 8 * 128 * 16;
+    if (L.bias_mma) w_off += 16 * L.N * 2;
     if (l > 0) { L.wt_off = wt_off; wt_off += CTX_MLP_W * 256 * 2; } else L.wt_off = -1;
     L.act_slot = slot; slot += 128 * L.N * 2;
     L.mask_slot = slot; slot += 128 * (L.N / 32) * 4;
@@ -121,6 +148,7 @@ extern "C" int ctx_mlp_describe(int D, uint32_t skip_mask, int in_pts, int in_vi
     F.n_x_pre = 0; F.n_h = h_chunks; F.n_x_post = 0; F.N = CTX_MLP_W; F.relu = 0; F.epi = CTX_EPI_HIDDEN;
     F.bias_off = f_off; f_off += F.N;
     F.w_off = w_off; w_off += F.n_h * CTX_MLP_KC * F.N * 2;
+    F.bias_mma = 1; F.bias_a_off = (CTX_MLP_XD_PAD - 16) / 8 * 128 * 16; w_off += 16 * F.N * 2;
     F.wt_off = wt_off; wt_off += CTX_MLP_W * 256 * 2;
     F.act_slot = slot; slot += 128 * F.N * 2;
     F.mask_slot = -1;
@@ -131,6 +159,7 @@ extern "C" int ctx_mlp_describe(int D, uint32_t skip_mask, int in_pts, int in_vi
     V.epi = CTX_EPI_FINAL_VIEWS;
     V.bias_off = f_off; f_off += V.N;
     V.w_off = w_off; w_off += (V.n_h + V.n_x_post) * CTX_MLP_KC * V.N * 2;
+    V.bias_mma = 0; V.bias_a_off = 0;
     V.wt_off = wt_off; wt_off += (CTX_MLP_W / 2) * 256 * 2;
     V.act_slot = slot; slot += 128 * V.N * 2;
     V.mask_slot = slot; slot += 128 * (V.N / 32) * 4;
@@ -163,10 +192,11 @@ extern "C" int ctx_mlp_pack(const void* net_host, const float* const* params, in
   memset(&a, 0, sizeof(a));
   a.n_layers = net.n_layers; a.w = (uint16_t*)wpacked; a.wt = (uint16_t*)wtpacked; a.fparams = fparams;
   a.has_views = views; a.out_ch = net.out_ch; a.head_off = net.head_off;
+  a.w_bytes = net.w_bytes; a.wt_bytes = net.wt_bytes;
   for (int l = 0; l < net.n_layers; ++l) {
     const CtxMlpLayer& L = net.L[l];
     ctx::PackLayer& P = a.L[l];
-    P.N = L.N; P.w_off = L.w_off; P.wt_off = L.wt_off; P.bias_off = L.bias_off;
+    P.N = L.N; P.w_off = L.w_off; P.wt_off = L.wt_off; P.bias_off = L.bias_off; P.bias_mma = L.bias_mma;
     int pi;
     if (l < D) pi = 2 * l;
     else if (l == D) pi = 2 * D;          // feature_linear

@@ -39,10 +39,16 @@ _SIGNATURES = {
     "ctx_mlp_describe": (c_int, [c_int, ctypes.c_uint32, c_int, c_int, c_int, P]),
     "ctx_mlp_pack": (c_int, [P, P, c_int, P, P, P, P]),
     "ctx_mlp_fwd": (c_int, [P, P, P, c_int, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int64, P, P, P]),
+    "ctx_mlp_fwd2": (c_int, [P, P, P, c_int, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int64, P, P, P]),
+    "ctx_mlp_set_prof_buffer": (c_int, [P]),
+    "ctx_mlp_set_debug": (c_int, [c_int]),
     "ctx_mlp_bwd": (c_int, [P, P, P, P, P, P, c_int64, P, c_int, P]),
     "ctx_adam_step": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_int, c_float, c_float, P]),
     "ctx_mse_fwd_bwd": (c_int, [P, P, P, c_int64, c_float, P, P, P, P]),
     "ctx_tcgen05_selftest": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
+    "ctx_tcgen05_mma_rate": (c_int, [c_int, c_int, c_int, c_int, P, c_int, P, P]),
+    "ctx_tcgen05_sync_cost": (c_int, [P, c_int, P]),
+    "ctx_tcgen05_selftest2": (c_int, [P, P, P, c_int, c_int, P]),
 }
 
 
@@ -79,7 +85,7 @@ def check(code: int, what: str) -> None:
 
 
 # kernels launched per ABI call (bench.py reports the total as gpu_launches)
-KERNELS_PER_CALL = {"ctx_mlp_bwd": 2}
+KERNELS_PER_CALL = {"ctx_mlp_bwd": 2, "ctx_mlp_fwd2": 2}
 launch_count = 0
 
 

@@ -69,8 +69,9 @@ class PackedWeights:
                 raise _lib.CtxNerfError("MLP parameters must be contiguous fp32 tensors on one CUDA device "
                                         "(ctxnerf has no CPU path)")
         if ent is None:
-            bufs = (torch.empty(d.w_bytes, dtype=torch.uint8, device=dev),
-                    torch.empty(max(d.wt_bytes, 16), dtype=torch.uint8, device=dev),
+            # two copies of each stream: whole-N chunks (cta_group::1 kernels) + half-split (2-CTA kernels)
+            bufs = (torch.empty(2 * d.w_bytes, dtype=torch.uint8, device=dev),
+                    torch.empty(max(2 * d.wt_bytes, 16), dtype=torch.uint8, device=dev),
                     torch.empty(d.n_fparams, dtype=torch.float32, device=dev))
         else:
             bufs = ent[1]
@@ -82,15 +83,22 @@ class PackedWeights:
         return bufs
 
 
+import os as _os
+
+# "2" = 2-CTA cta_group::2 ping-pong kernels (default), "1" = single-CTA kernels
+KERNEL_VERSION = _os.environ.get("CTXNERF_MLP_KERNEL", "2")
+
+
 def _launch_fwd(desc: NetDesc, w, f, *, x=None, rays=None, P: int, out, acts=None, L_pts=10, L_dirs=4):
     dev = out.device
+    fn = "ctx_mlp_fwd2" if KERNEL_VERSION == "2" else "ctx_mlp_fwd"
     with torch.cuda.device(dev):
         if x is not None:
-            call("ctx_mlp_fwd", desc.p, ptr(w), ptr(f), 0, ptr(x), x.shape[-1], None, None, None, None, 0, 0, 0, P,
+            call(fn, desc.p, ptr(w), ptr(f), 0, ptr(x), x.shape[-1], None, None, None, None, 0, 0, 0, P,
                  ptr(out), ptr(acts), stream_ptr(dev))
         else:
             o, d, v, z = rays
-            call("ctx_mlp_fwd", desc.p, ptr(w), ptr(f), 1, None, 0, ptr(o), ptr(d), ptr(v), ptr(z), z.shape[-1],
+            call(fn, desc.p, ptr(w), ptr(f), 1, None, 0, ptr(o), ptr(d), ptr(v), ptr(z), z.shape[-1],
                  L_pts, L_dirs, P, ptr(out), ptr(acts), stream_ptr(dev))
 
 
@@ -111,8 +119,7 @@ def forward_raw(module, *, x=None, rays=None, save_acts=False):
     out = torch.empty(P, desc.out_ch, device=dev, dtype=torch.float32)
     acts = None
     if save_acts:
-        ntiles = (P + TILE - 1) // TILE
-        ntiles += ntiles & 1
+        ntiles = 4 * ((P + 4 * TILE - 1) // (4 * TILE))     # the 2-CTA kernels work on 4 tiles at a time
         acts = torch.empty(ntiles * desc.act_tile_bytes, dtype=torch.uint8, device=dev)
     _launch_fwd(desc, w, f, x=x, rays=rays, P=P, out=out, acts=acts, L_pts=module.L_pts, L_dirs=module.L_dirs)
     return out, acts, P, packed
@@ -123,8 +130,7 @@ class _MlpFn(torch.autograd.Function):
     data: encodings of fixed coordinates)."""
 
     @staticmethod
-    def forward(ctx, module, x, rays, *params):
-        need_grad = any(ctx.needs_input_grad[3:])
+    def forward(ctx, module, x, rays, need_grad, *params):
         lead = x.shape[:-1] if x is not None else rays[3].shape
         out, acts, P, packed = forward_raw(module, x=x, rays=rays, save_acts=need_grad)
         ctx.module, ctx.P, ctx.acts, ctx.packed = module, P, acts, packed
@@ -135,7 +141,7 @@ class _MlpFn(torch.autograd.Function):
         from .mlp_bwd import mlp_backward
         grads = mlp_backward(ctx.module, ctx.packed, ctx.acts, ctx.P, g_out)
         ctx.acts = None
-        return (None, None, None) + tuple(grads)
+        return (None, None, None, None) + tuple(grads)
 
 
 class FusedMLPBase(nn.Module):
@@ -161,4 +167,6 @@ class FusedMLPBase(nn.Module):
 
     def _run(self, x=None, rays=None):
         self._ensure()
-        return _MlpFn.apply(self, x, rays, *self._param_list())
+        params = self._param_list()
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _MlpFn.apply(self, x, rays, need_grad, *params)

@@ -101,10 +101,12 @@ class _Composite(torch.autograd.Function):
         R, S, white, has_noise, raw_shape = ctx.meta
         g_raw = torch.empty_like(raw_c)
         dev = raw_c.device
+        # keep every (possibly converted) gradient tensor referenced until the launch is enqueued
+        gs = [_f32c(g_rgb), _f32c(g_disp), _f32c(g_acc), _f32c(g_weights), _f32c(g_depth)]
         with torch.cuda.device(dev):
             call("ctx_composite_bwd", ptr(raw_c), ptr(z_c), ptr(d_c), ptr(n_c if has_noise else None),
-                 R, S, int(white), ptr(_f32c(g_rgb)), ptr(_f32c(g_disp)), ptr(_f32c(g_acc)),
-                 ptr(_f32c(g_weights)), ptr(_f32c(g_depth)), ptr(g_raw), stream_ptr(dev))
+                 R, S, int(white), ptr(gs[0]), ptr(gs[1]), ptr(gs[2]), ptr(gs[3]), ptr(gs[4]), ptr(g_raw),
+                 stream_ptr(dev))
         return g_raw.reshape(raw_shape), None, None, None, None
 
 
@@ -236,10 +238,11 @@ def raygen(H, W, K, c2w, *, device=None, ray_idx=None, ndc=None, n_samples=0, ne
     import ctypes
     sph = (ctypes.c_float * 4)(*[float(s) for s in sphere]) if sphere is not None else None
     use_ndc, nfoc, nnear = (1, float(ndc[0]), float(ndc[1])) if ndc is not None else (0, 0.0, 0.0)
+    jitter = _f32c(jitter)
     with torch.cuda.device(dev):
         call("ctx_raygen_fwd", int(H), int(W), fx, fy, cx, cy, ptr(c2w_d), int(ld), ptr(ray_idx), n, use_ndc,
              nfoc, nnear, int(n_samples), float(near), float(far), int(lindisp), int(bool(perturb)),
-             ptr(_f32c(jitter)), int(seed or 0), int(sphere is not None),
+             ptr(jitter), int(seed or 0), int(sphere is not None),
              ctypes.cast(sph, ctypes.c_void_p) if sph is not None else None,
              ptr(o), ptr(d), ptr(v), ptr(z), ptr(nf), stream_ptr(dev))
     return {"rays_o": o, "rays_d": d, "viewdirs": v, "z_vals": z, "near_far": nf}
@@ -255,10 +258,11 @@ def stratified(near, far, n_samples, lindisp=False, perturb=False, jitter=None, 
     z = torch.empty(R, n_samples, device=dev, dtype=torch.float32)
     if perturb and jitter is None and seed is None:
         seed = new_seed()
+    jitter = _f32c(jitter)
     with torch.cuda.device(dev):
         call("ctx_stratified_fwd", ptr(near), near.stride(0) if R > 1 else 1, ptr(far),
              far.stride(0) if R > 1 else 1, R, int(n_samples), int(lindisp), int(bool(perturb)),
-             ptr(_f32c(jitter)), int(seed or 0), ptr(z), stream_ptr(dev))
+             ptr(jitter), int(seed or 0), ptr(z), stream_ptr(dev))
     return z
 
 
@@ -282,8 +286,9 @@ class _Ndc(torch.autograd.Function):
         o, d = ctx.saved_tensors
         H, W, focal, near, shape = ctx.meta
         go, gd = torch.empty_like(o), torch.empty_like(d)
+        g_o, g_d = _f32c(g_o), _f32c(g_d)
         with torch.cuda.device(d.device):
-            call("ctx_ndc_bwd", H, W, focal, near, ptr(o), ptr(d), ptr(_f32c(g_o)), ptr(_f32c(g_d)), o.shape[0],
+            call("ctx_ndc_bwd", H, W, focal, near, ptr(o), ptr(d), ptr(g_o), ptr(g_d), o.shape[0],
                  ptr(go), ptr(gd), stream_ptr(d.device))
         return None, None, None, None, go.reshape(shape), gd.reshape(shape)
 

@@ -321,8 +321,10 @@ def _q(t: torch.Tensor) -> torch.Tensor:
 
 
 def mlp_forward_bf16(p, x, D=8, skips=(4,), input_ch_views=0):
-    """mlp_forward with every matmul operand rounded to bf16 (fp32 accumulate,
-    fp32 bias add) -- the arithmetic of the tcgen05 kernel."""
+    """mlp_forward with every matmul operand rounded to bf16, fp32 accumulate --
+    the arithmetic of the tcgen05 kernel.  The biases of the GEMM layers are bf16
+    too (the 2-CTA kernel feeds them through the MMA on a constant-1 input
+    channel); the small heads (alpha, rgb, output) keep fp32 biases."""
     if input_ch_views > 0:
         pts, views = x[..., :-input_ch_views], x[..., -input_ch_views:]
     else:
@@ -330,16 +332,16 @@ def mlp_forward_bf16(p, x, D=8, skips=(4,), input_ch_views=0):
     pts_q = _q(pts)
     h = pts_q
     for l in range(D):
-        h = torch.relu(h @ _q(p[f"pts_linears.{l}.weight"]).T + p[f"pts_linears.{l}.bias"])
+        h = torch.relu(h @ _q(p[f"pts_linears.{l}.weight"]).T + _q(p[f"pts_linears.{l}.bias"]))
         h = _q(h)
         if l in skips:
             h = torch.cat([pts_q, h], -1)
     if views is None:
         return h @ _q(p["output_linear.weight"]).T + p["output_linear.bias"]
     alpha = h @ _q(p["alpha_linear.weight"]).T + p["alpha_linear.bias"]
-    feat = _q(h @ _q(p["feature_linear.weight"]).T + p["feature_linear.bias"])
+    feat = _q(h @ _q(p["feature_linear.weight"]).T + _q(p["feature_linear.bias"]))
     hv = torch.cat([feat, _q(views)], -1)
-    hv = _q(torch.relu(hv @ _q(p["views_linears.0.weight"]).T + p["views_linears.0.bias"]))
+    hv = _q(torch.relu(hv @ _q(p["views_linears.0.weight"]).T + _q(p["views_linears.0.bias"])))
     rgb = hv @ _q(p["rgb_linear.weight"]).T + p["rgb_linear.bias"]
     return torch.cat([rgb, alpha], -1)
 

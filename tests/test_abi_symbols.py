@@ -51,7 +51,8 @@ def test_mlp_describe_matches_the_reference_layer_structure(libpath):
     d = NetDesc(8, [4], 63, 0, 4)
     assert d.n_layers == 8
     # forward stream: L0 64x256, 7 hidden 256x256 (+64 on the skip layer), bf16
-    assert d.w_bytes == 2 * 256 * (64 + 7 * 256 + 64)
+    # (+ one 16-wide bias chunk for each of the 6 layers that do not read the x buffer)
+    assert d.w_bytes == 2 * 256 * (64 + 7 * 256 + 64) + 6 * 2 * 256 * 16
     v = NetDesc(8, [4], 63, 27, 4)
     assert v.n_layers == 10
-    assert v.w_bytes == d.w_bytes + 2 * (256 * 256 + 128 * (256 + 32))
+    assert v.w_bytes == d.w_bytes + 2 * (256 * 256 + 128 * (256 + 32)) + 2 * 256 * 16
