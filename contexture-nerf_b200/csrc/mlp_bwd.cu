@@ -19,6 +19,11 @@
 // /root/reference/src/run_nerf_helpers.py:106-135.
 #include "mlp_common.cuh"
 #include <string.h>
+#include <stdlib.h>
+
+// 2-CTA dgrad (mlp_bwd2.cu)
+int ctx_launch_dgrad2(const CtxMlpNet& net, const void* wtpacked, const float* fparams, const float* g_out,
+                      const void* acts, void* dacts, int64_t P, cudaStream_t st);
 
 namespace ctx {
 
@@ -447,7 +452,11 @@ extern "C" int ctx_mlp_bwd(const void* net_host, const void* wtpacked, const flo
     attr_set = true;
   }
   // ---------------- dgrad ----------------
-  {
+  static const bool use_v1 = [] { const char* e = getenv("CTXNERF_MLP_KERNEL"); return e && e[0] == '1'; }();
+  if (!use_v1) {
+    const int rc = ctx_launch_dgrad2(net, wtpacked, fparams, g_out, acts, dacts, P, st);
+    if (rc != 0) return rc;
+  } else {
     ctx::DgradArgs a;
     a.net = net; a.wtpacked = (const uint8_t*)wtpacked; a.fparams = fparams; a.g_out = g_out;
     a.acts = (const uint8_t*)acts; a.dacts = (uint8_t*)dacts; a.P = P;
