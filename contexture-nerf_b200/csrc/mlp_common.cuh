@@ -11,7 +11,6 @@ namespace ctx {
 
 constexpr int kTileM = 128;
 constexpr int kTiles = 2;
-constexpr int kStages = 4;
 constexpr int kStageBytes = CTX_MLP_W * CTX_MLP_KC * 2;   // 16 KB
 constexpr int kHBytes = kTileM * CTX_MLP_W * 2;            // 64 KB
 constexpr int kXBytes = kTileM * CTX_MLP_XP_PAD * 2;       // 16 KB
@@ -35,13 +34,6 @@ struct MlpFwdArgs {
   int debug;                // diagnostics: 1 = epilogue skips TMEM loads/stores, 2 = issuer skips the MMAs
 };
 
-struct __align__(8) MlpSmemCtl {
-  uint64_t full[kStages], empty[kStages];
-  uint64_t acc_full[kTiles], act_ready[kTiles];
-  uint32_t tmem_base;
-};
-
-constexpr size_t kMlpSmemBytes = (size_t)kTiles * (kHBytes + kXBytes) + (size_t)kStages * kStageBytes + 256;
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
@@ -65,10 +57,12 @@ __device__ __forceinline__ void fast_sincos(float a, float& s, float& c) {
 }
 
 // write 8 consecutive channels [ch0, ch0+8) of row `row` of a K-major A tile; `gtile` (nullable) is the
-// same tile image in HBM (activation / dZ record): the 16-byte row chunk is mirrored there straight from
-// registers (a warp covers 512 contiguous bytes), so saving activations needs no extra pass over shared memory
+// record of the same tile in HBM (activation / dZ record, `gC` channels wide): the 16-byte row chunk is
+// mirrored there straight from registers (a warp covers 512 contiguous bytes), so saving activations needs
+// no extra pass over shared memory.  Record layout: two 64-point halves, each [gC/8][64 points][8 channels]
+// -- a half is one contiguous bulk-TMA unit of the wgrad kernel (MN-major operand, K = points).
 __device__ __forceinline__ void store_row8(uint8_t* tile, int row, int ch0, const float* v, bool relu,
-                                           uint8_t* gtile = nullptr) {
+                                           uint8_t* gtile = nullptr, int gC = 0) {
   uint4 q;
   if (relu) {
     q.x = pack_bf16x2_relu(v[0], v[1]); q.y = pack_bf16x2_relu(v[2], v[3]);
@@ -77,9 +71,10 @@ __device__ __forceinline__ void store_row8(uint8_t* tile, int row, int ch0, cons
     q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
     q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
   }
-  const uint32_t off = (ch0 >> 3) * kK8Stride + (row >> 3) * 128 + (row & 7) * 16;
-  if (tile) *reinterpret_cast<uint4*>(tile + off) = q;
-  if (gtile) *reinterpret_cast<uint4*>(gtile + off) = q;
+  if (tile) *reinterpret_cast<uint4*>(tile + (ch0 >> 3) * kK8Stride + (row >> 3) * 128 + (row & 7) * 16) = q;
+  if (gtile)
+    *reinterpret_cast<uint4*>(gtile + (row >> 6) * (gC * 128) + (ch0 >> 3) * 1024 + ((row & 63) >> 3) * 128 +
+                              (row & 7) * 16) = q;
 }
 
 }  // namespace ctx

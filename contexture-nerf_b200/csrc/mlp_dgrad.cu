@@ -1,6 +1,6 @@
-// dgrad of the coordinate MLP, 2-CTA version (tcgen05.mma.cta_group::2 + ping-pong).
+// dgrad of the coordinate MLP on tcgen05 / TMEM: 2-CTA MMAs (cta_group::2) + ping-pong.
 //
-// Same machinery as mlp_fwd2.cu run backwards: a cluster of two CTAs owns 512
+// Same machinery as mlp_fwd.cu run backwards: a cluster of two CTAs owns 512
 // points per iteration as two 256-row tile pairs; for every step (layer l, last
 // to first) dH = dZ_l * W_l is one chain of M=256 MMAs over the half-split
 // transposed weight stream, and the epilogue of one tile pair (ReLU sign mask
@@ -20,7 +20,7 @@ constexpr int kDgPairs = kDgStages / 2;
 constexpr int kDgStageBytes = 8192;          // 128 in-feature rows x 32 K x 2 B
 constexpr int kDgHeadFloats = 1028;
 
-struct DgradArgs2 {
+struct DgradArgs {
   CtxMlpNet net;
   const uint8_t* wtstream;   // half-split transposed stream
   const float* fparams;
@@ -33,21 +33,21 @@ struct DgradArgs2 {
   int step_dst[CTX_MLP_MAX_LAYERS];
 };
 
-struct __align__(8) Dg2SmemCtl {
+struct __align__(8) DgSmemCtl {
   uint64_t full[kDgPairs], empty[kDgPairs], peer_full[kDgPairs];
   uint64_t acc_full[kTiles], act_ready[kTiles];
   uint32_t tmem_base;
 };
 // two 64 KB dZ tiles + weight ring + head weights (fp32) + barriers
-constexpr size_t kDg2SmemBytes = (size_t)kTiles * kHBytes + (size_t)kDgStages * kDgStageBytes + kDgHeadFloats * 4 + 256;
+constexpr size_t kDgSmemBytes = (size_t)kTiles * kHBytes + (size_t)kDgStages * kDgStageBytes + kDgHeadFloats * 4 + 256;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
-mlp_dgrad2_kernel(const __grid_constant__ DgradArgs2 a) {
+mlp_dgrad_kernel(const __grid_constant__ DgradArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* h_buf = smem;
   uint8_t* w_buf = smem + kTiles * kHBytes;
   float* s_head = reinterpret_cast<float*>(w_buf + kDgStages * kDgStageBytes);
-  Dg2SmemCtl* ctl = reinterpret_cast<Dg2SmemCtl*>(s_head + kDgHeadFloats);
+  DgSmemCtl* ctl = reinterpret_cast<DgSmemCtl*>(s_head + kDgHeadFloats);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t r = tc::cluster_ctarank();
@@ -194,8 +194,8 @@ mlp_dgrad2_kernel(const __grid_constant__ DgradArgs2 a) {
         float gv[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) gv[i] = i < 4 ? g[i] : 0.f;
-        store_row8(nullptr, row, 0, gv, false, drec + gout_slot);
-        store_row8(nullptr, row, 8, gv + 8, false, drec + gout_slot);
+        store_row8(nullptr, row, 0, gv, false, drec + gout_slot, 16);
+        store_row8(nullptr, row, 8, gv + 8, false, drec + gout_slot, 16);
       }
       const int nw = lastN / 32;
       const uint32_t* mrow = reinterpret_cast<const uint32_t*>(rec + last_mask) + row * nw;
@@ -219,7 +219,7 @@ mlp_dgrad2_kernel(const __grid_constant__ DgradArgs2 a) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = ((neg >> (31 - j)) & 1u) ? 0.f : v[j];
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) store_row8(my_h, row, cb * 32 + j, v + j, false, drec + last_act);
+        for (int j = 0; j < 32; j += 8) store_row8(my_h, row, cb * 32 + j, v + j, false, drec + last_act, lastN);
       }
     };
 
@@ -266,7 +266,7 @@ mlp_dgrad2_kernel(const __grid_constant__ DgradArgs2 a) {
             }
 #pragma unroll
             for (int j = 0; j < 32; j += 8)
-              store_row8(has_next ? my_h : nullptr, row, cb * 32 + j, v + j, false, drec + Dact);
+              store_row8(has_next ? my_h : nullptr, row, cb * 32 + j, v + j, false, drec + Dact, 256);
           }
           if (has_next) {
             arrive_act(ph);
@@ -291,25 +291,25 @@ mlp_dgrad2_kernel(const __grid_constant__ DgradArgs2 a) {
 
 }  // namespace ctx
 
-// host launcher used by ctx_mlp_bwd (mlp_bwd.cu)
-int ctx_launch_dgrad2(const CtxMlpNet& net, const void* wtpacked, const float* fparams, const float* g_out,
+// host launcher used by ctx_mlp_bwd (mlp_wgrad.cu)
+int ctx_launch_dgrad(const CtxMlpNet& net, const void* wtpacked, const float* fparams, const float* g_out,
                       const void* acts, void* dacts, int64_t P, cudaStream_t st) {
-  ctx::DgradArgs2 a;
+  ctx::DgradArgs a;
   a.net = net;
-  a.wtstream = (const uint8_t*)wtpacked + net.wt_bytes;
+  a.wtstream = (const uint8_t*)wtpacked;
   a.fparams = fparams; a.g_out = g_out; a.acts = (const uint8_t*)acts; a.dacts = (uint8_t*)dacts; a.P = P;
   int n = 0;
   for (int l = net.n_layers - 1; l >= 1; --l) { a.step_src[n] = l; a.step_dst[n] = l - 1; ++n; }
   a.n_steps = n;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(ctx::mlp_dgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)ctx::kDg2SmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(ctx::mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)ctx::kDgSmemBytes);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const int64_t citers = ctx::ceil_div(P, (int64_t)ctx::kTileM * 4);
   const int ncl = (int)(citers < ctx::kNumSMs / 2 ? citers : ctx::kNumSMs / 2);
-  ctx::mlp_dgrad2_kernel<<<2 * ncl, ctx::kMlpThreads, ctx::kDg2SmemBytes, st>>>(a);
+  ctx::mlp_dgrad_kernel<<<2 * ncl, ctx::kMlpThreads, ctx::kDgSmemBytes, st>>>(a);
   return (int)cudaGetLastError();
 }

@@ -1,296 +1,437 @@
-// Fused coordinate-MLP forward on tcgen05 / TMEM (sm_100a).
+// Fused coordinate-MLP forward on tcgen05 / TMEM (sm_100a): 2-CTA MMAs (cta_group::2) + ping-pong.
 //
-// One persistent CTA per SM.  Per iteration a CTA owns 256 points = two
-// 128-row accumulator tiles (2 x 256 TMEM columns).  For every layer the weight
-// matrix is streamed ONCE per iteration from L2 in 16 KB K-chunks by 1-D bulk
-// TMA copies (4-stage mbarrier ring) and each chunk feeds the MMAs of both
-// tiles; activations never leave the SM: the epilogue warps read the fp32
-// accumulator from TMEM, add the bias, apply ReLU, round to bf16 and write the
-// next layer's A operand straight back into shared memory.  The positional
-// encoding of the points (o + d*z, L=10) and of the view directions (L=4) is
-// produced directly in shared memory as the layer-0 / view-layer A operand.
-// The 1- to 4-wide heads (alpha, rgb, output_linear) are folded into the
-// preceding epilogue on the CUDA cores.
+// A cluster of two CTAs (one SM pair) owns 512 points per iteration, arranged as
+// two 256-row tile pairs A and B (each CTA holds 128 rows of A and 128 rows of B,
+// i.e. two 128x256 fp32 accumulators = all 512 TMEM columns).  Every
+// MMA is M=256 across the pair: each CTA feeds its own 128 activation rows and
+// HALF of the weight rows (N/2), so per CTA the B-operand shared-memory reads and
+// the weight staging are halved with respect to cta_group::1.  Layers alternate
+// between the tile pairs,
+//     MMA(l, A) | MMA(l, B) | MMA(l+1, A) | ...
+//                 epi(l, A) | epi(l, B)   | ...
+// so the TMEM->bias->ReLU->bf16->shared-memory epilogue of one pair (and, when
+// training, the activation-record stores) runs under the MMAs of the other one.
+// Weights are streamed twice per layer (once per pair) as 8 KB half-chunks by
+// 1-D bulk TMA through an 8-stage ring (1.2 MB of L2 reads per CTA per 256 points).
 //
-// Warp roles (320 threads): warp 0 = weight-stream producer (one lane),
-// warp 1 = TMEM allocator + MMA issuer (one lane), warps 2-9 = encode/epilogue
-// (4 warps per tile; warp%4 selects the TMEM lane quarter).
+// Synchronisation: full/empty/acc_full barriers are local to each CTA (the MMA
+// completion is multicast to both with tcgen05.commit...multicast::cluster); the
+// leader's MMA thread additionally needs (a) the peer's weight half landed --
+// relayed by the peer's otherwise idle warp 1 with a remote mbarrier arrive -- and
+// (b) both CTAs' epilogue warps done with the next A operand (act_ready, 16 warp
+// arrivals, the peer's are remote).
 //
 // Reference semantics: NeRF2D.forward, /root/reference/src/run_nerf_helpers.py:106-135
-// (and the commented view branch :117-127); Embedder.embed :44-45.
+// (+ commented view branch :117-127); Embedder.embed :44-45.
 #include "mlp_common.cuh"
 
 namespace ctx {
 
-// encode d-dim coordinate vector into channels [x | sin f0 x | cos f0 x | ...] padded with zeros to `pad`
+constexpr int kStages2 = 8;          // 8 KB half-chunk stages, handled in PAIRS (one full/empty barrier per pair)
+constexpr int kPairs2 = kStages2 / 2;
+constexpr int kHeadFloats = 648;    // view-direction head block staged in shared memory (w_alpha, W_rgb, biases)
+constexpr int kStage2Bytes = kStageBytes / 2;   // 8 KB half-chunk
+
+struct __align__(8) Mlp2SmemCtl {
+  uint64_t full[kPairs2], empty[kPairs2], peer_full[kPairs2];
+  uint64_t acc_full[kTiles], act_ready[kTiles];
+  uint32_t tmem_base;
+};
+constexpr size_t kMlp2SmemBytes = (size_t)kTiles * (kHBytes + kXBytes) + (size_t)kStages2 * kStage2Bytes +
+                                  kHeadFloats * 4 + 256;
+
 template <int PAD, int MAXL>
-__device__ __forceinline__ void encode_row(uint8_t* tile, int row, const float* xyz, int L, bool valid,
-                                           uint8_t* gtile) {
-  constexpr int d = 3;
+__device__ __forceinline__ void encode_row2(uint8_t* tile, int row, const float* xyz, int L, bool valid,
+                                            uint8_t* gtile) {
   float v[PAD];
 #pragma unroll
   for (int i = 0; i < PAD; ++i) v[i] = 0.f;
   if (valid) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j)
-      if (j < d) v[j] = xyz[j];
+    for (int j = 0; j < 3; ++j) v[j] = xyz[j];
 #pragma unroll
     for (int k = 0; k < MAXL; ++k) {
       if (k < L) {
         const float f = (float)(1 << k);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          if (j < d) {
-            float s, c;
-            fast_sincos(xyz[j] * f, s, c);
-            const int b = d + k * 2 * d;
-            if (b + d + j < PAD) { v[b + j] = s; v[b + d + j] = c; }
-          }
+          float s, c;
+          fast_sincos(xyz[j] * f, s, c);
+          const int b = 3 + k * 6;
+          if (b + 3 + j < PAD) { v[b + j] = s; v[b + 3 + j] = c; }
         }
       }
     }
   }
+  v[PAD - 1] = 1.0f;   // constant-1 channel: carries the bias through the GEMM
 #pragma unroll
-  for (int c0 = 0; c0 < PAD; c0 += 8) store_row8(tile, row, c0, v + c0, false, gtile);
+  for (int c0 = 0; c0 < PAD; c0 += 8) store_row8(tile, row, c0, v + c0, false, gtile, PAD);
 }
 
-__global__ void __launch_bounds__(kMlpThreads, 1) mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
+template <bool kProf>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
+mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
+#define PCLK() (kProf ? clock64() : 0ll)
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* h_buf = smem;                                          // kTiles x 64 KB
-  uint8_t* x_buf = smem + kTiles * kHBytes;                       // kTiles x 16 KB
-  uint8_t* w_buf = x_buf + kTiles * kXBytes;                      // kStages x 16 KB
-  MlpSmemCtl* ctl = reinterpret_cast<MlpSmemCtl*>(w_buf + kStages * kStageBytes);
+  uint8_t* h_buf = smem;
+  uint8_t* x_buf = smem + kTiles * kHBytes;
+  uint8_t* w_buf = x_buf + kTiles * kXBytes;
+  float* s_head = reinterpret_cast<float*>(w_buf + kStages2 * kStage2Bytes);   // head weights, loaded once
+  Mlp2SmemCtl* ctl = reinterpret_cast<Mlp2SmemCtl*>(s_head + kHeadFloats);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t r = tc::cluster_ctarank();
   const CtxMlpNet& net = a.net;
-  const int64_t n_iters_total = ceil_div(a.P, (int64_t)kTileM * kTiles);
+  const int64_t n_citers = ceil_div(a.P, (int64_t)kTileM * 4);
+  const int64_t cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  const uint8_t* wstream = a.wpacked;   // half-split chunk layout (mlp_pack.cu)
 
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) { tc::mbar_init(&ctl->full[s], 1); tc::mbar_init(&ctl->empty[s], 1); }
-    for (int t = 0; t < kTiles; ++t) {
-      tc::mbar_init(&ctl->acc_full[t], 1);
-      tc::mbar_init(&ctl->act_ready[t], kEpiThreadsPerTile);
+    for (int s = 0; s < kPairs2; ++s) {
+      tc::mbar_init(&ctl->full[s], 1); tc::mbar_init(&ctl->empty[s], 1); tc::mbar_init(&ctl->peer_full[s], 1);
     }
+    for (int t = 0; t < kTiles; ++t) { tc::mbar_init(&ctl->acc_full[t], 1); tc::mbar_init(&ctl->act_ready[t], 16); }
     tc::mbar_fence_init();
   }
-  if (warp == 1) tc::tmem_alloc(&ctl->tmem_base, 512);
+  if (warp == 1) tc::tmem_alloc2(&ctl->tmem_base, 512);
+  {
+    if (net.in_views > 0)
+      for (int i = tid; i < kHeadFloats; i += kMlpThreads) s_head[i] = a.fparams[net.head_off + i];
+  }
   tc::tc_fence_before();
-  __syncthreads();
+  tc::cluster_sync_all();
   tc::tc_fence_after();
   const uint32_t tmem = ctl->tmem_base;
 
   if (warp == 0) {
-    // ===================== weight-stream producer =====================
-    if (lane == 0) {
-      uint32_t g = 0;  // running chunk counter
-      for (int64_t it = blockIdx.x; it < n_iters_total; it += gridDim.x) {
+    // ============ weight-stream producer: this CTA's half of every chunk, twice per layer ============
+    // chunks are staged in pairs: one expect_tx / full barrier covers two consecutive 8 KB stages
+    {
+      uint32_t g = 0;
+      for (int64_t it = cid; it < n_citers; it += ncl) {
         for (int l = 0; l < net.n_layers; ++l) {
-          const CtxMlpLayer& L = net.L[l];
-          const int nchunks = L.n_x_pre + L.n_h + L.n_x_post;
-          const uint32_t bytes = (uint32_t)L.N * CTX_MLP_KC * 2;
-          for (int c = 0; c < nchunks; ++c, ++g) {
-            const int s = g % kStages;
-            const uint32_t ph = (g / kStages) & 1;
-            tc::mbar_wait(&ctl->empty[s], ph ^ 1);
-            tc::mbar_arrive_expect_tx(&ctl->full[s], bytes);
-            tc::bulk_g2s(w_buf + s * kStageBytes, a.wpacked + L.w_off + (size_t)c * bytes, bytes, &ctl->full[s]);
+          // (layer fields are copied to registers: the asm memory clobbers would otherwise force a
+          //  constant-bank reload of every field on every chunk)
+          const int nchunks = net.L[l].n_x_pre + net.L[l].n_h + net.L[l].n_x_post;
+          const int ntot = nchunks + net.L[l].bias_mma;
+          const uint32_t half = (uint32_t)net.L[l].N * CTX_MLP_KC;   // (N/2 rows) x 32 K x 2 B
+          const uint8_t* lsrc = wstream + net.L[l].w_off;
+          for (int ph = 0; ph < 2; ++ph) {
+            for (int c = 0; c < ntot; ++c, ++g) {
+              const int s = g % kStages2, pr = s >> 1;
+              // regular chunk: 32 K ; trailing bias chunk (c == nchunks): 16 K
+              const uint32_t bytes = c < nchunks ? half : half / 2;
+              if (!(g & 1)) tc::mbar_wait(&ctl->empty[pr], ((g / kStages2) & 1) ^ 1);
+              if (tc::elect_one()) {
+                tc::mbar_expect_tx(&ctl->full[pr], bytes);
+                tc::bulk_g2s(w_buf + s * kStage2Bytes, lsrc + (size_t)c * 2 * half + r * bytes, bytes, &ctl->full[pr]);
+                if (g & 1) tc::mbar_arrive(&ctl->full[pr]);
+              }
+              __syncwarp();
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ========================= MMA issuer ==============================
-    if (lane == 0) {
-      uint32_t g = 0;
-      uint32_t act_phase = 0;  // same sequence for both tiles
-      for (int64_t it = blockIdx.x; it < n_iters_total; it += gridDim.x) {
-        for (int l = 0; l < net.n_layers; ++l) {
-          const CtxMlpLayer& L = net.L[l];
-          const int nchunks = L.n_x_pre + L.n_h + L.n_x_post;
-          const uint32_t idesc = tc::make_idesc_bf16(kTileM, L.N, 0, 0);
-          const uint32_t b_lbo = (uint32_t)L.N * 16;
-          for (int c = 0; c < nchunks; ++c, ++g) {
-            const int s = g % kStages;
-            tc::mbar_wait(&ctl->full[s], (g / kStages) & 1);
-            tc::tc_fence_after();
-            // A source of this chunk
-            uint32_t a_off;  // byte offset inside the tile's buffers
-            bool from_x;
-            if (c < L.n_x_pre) { from_x = true; a_off = c * 4 * kK8Stride; }
-            else if (c < L.n_x_pre + L.n_h) { from_x = false; a_off = (c - L.n_x_pre) * 4 * kK8Stride; }
-            else { from_x = true; a_off = (c - L.n_x_pre - L.n_h) * 4 * kK8Stride; }
-            const uint32_t b_base = tc::smem_u32(w_buf + s * kStageBytes);
-#pragma unroll
-            for (int t = 0; t < kTiles; ++t) {
-              if (c == 0) {
-                tc::mbar_wait(&ctl->act_ready[t], act_phase);
-                tc::tc_fence_after();
+    {
+      if (r != 0) {
+        // ============ peer CTA: relay "my half landed" to the leader ============
+        uint32_t g = 0;
+        for (int64_t it = cid; it < n_citers; it += ncl)
+          for (int l = 0; l < net.n_layers; ++l) {
+            const int nchunks = net.L[l].n_x_pre + net.L[l].n_h + net.L[l].n_x_post + net.L[l].bias_mma;
+            for (int c = 0; c < 2 * nchunks; ++c, ++g) {
+              if (g & 1) {   // one relay per chunk pair
+                const int pr = (g % kStages2) >> 1;
+                tc::mbar_wait(&ctl->full[pr], (g / kStages2) & 1);
+                if (tc::elect_one()) tc::mbar_arrive_remote(&ctl->peer_full[pr], 0);
+                __syncwarp();
               }
-              const uint32_t a_base = tc::smem_u32(from_x ? (x_buf + t * kXBytes) : (h_buf + t * kHBytes)) + a_off;
-#pragma unroll
-              for (int kk = 0; kk < 2; ++kk) {
-                const uint64_t da = tc::make_smem_desc(a_base + kk * 2 * kK8Stride, kK8Stride, 128);
-                const uint64_t db = tc::make_smem_desc(b_base + kk * 2 * b_lbo, b_lbo, 128);
-                tc::mma_bf16_ss(tmem + t * CTX_MLP_W, da, db, idesc, (c > 0 || kk > 0) ? 1u : 0u);
-              }
-              if (c == nchunks - 1) tc::mma_commit(&ctl->acc_full[t]);
             }
-            tc::mma_commit(&ctl->empty[s]);
           }
-          act_phase ^= 1;
+      } else {
+        // ============ leader CTA: MMA issuer for the pair ============
+        // one barrier round trip per PAIR of chunks (4 MMAs): the single issuing thread has to stay
+        // ahead of the tensor pipe (128 cycles per MMA), so per-chunk polling is too expensive
+        uint32_t g = 0, act_phase[2] = {0, 0};
+        const int dbg = a.debug;
+        long long t_act = 0, t_full = 0, t_peer = 0, t_issue = 0, t_ldc = 0;
+        const long long t_begin = PCLK();
+        for (int64_t it = cid; it < n_citers; it += ncl) {
+          for (int l = 0; l < net.n_layers; ++l) {
+            const long long c0 = PCLK();
+            const int n_x_pre = net.L[l].n_x_pre, n_h = net.L[l].n_h, n_x_post = net.L[l].n_x_post;
+            const int bias_mma = net.L[l].bias_mma, bias_a_off = net.L[l].bias_a_off, LN = net.L[l].N;
+            const int nchunks = n_x_pre + n_h + n_x_post;
+            if (kProf) { asm volatile("" ::"r"(nchunks + bias_mma + bias_a_off + LN)); t_ldc += PCLK() - c0; }
+            const uint32_t idesc = tc::make_idesc_bf16(256, LN, 0, 0);
+            const uint32_t b_lbo = (uint32_t)(LN / 2) * 16;
+#pragma unroll
+            for (int ph = 0; ph < 2; ++ph) {
+              long long w0 = PCLK();
+              tc::mbar_wait(&ctl->act_ready[ph], act_phase[ph]);
+              t_act += PCLK() - w0;
+              act_phase[ph] ^= 1;
+              tc::tc_fence_after();
+              const int ntot = nchunks + bias_mma;
+              const uint32_t x_base = tc::smem_u32(x_buf + ph * kXBytes), h_base = tc::smem_u32(h_buf + ph * kHBytes);
+              for (int c = 0; c < ntot; ++c, ++g) {
+                const int s = g % kStages2, pr = s >> 1;
+                if (!(g & 1)) {
+                  const uint32_t par = (g / kStages2) & 1;
+                  w0 = PCLK();
+                  tc::mbar_wait(&ctl->full[pr], par);
+                  const long long w1 = PCLK();
+                  if (!(dbg & 4)) tc::mbar_wait(&ctl->peer_full[pr], par);
+                  const long long w2 = PCLK();
+                  t_full += w1 - w0; t_peer += w2 - w1;
+                  tc::tc_fence_after();
+                }
+                w0 = PCLK();
+                uint32_t a_base;
+                if (c < n_x_pre) a_base = x_base + c * 4 * kK8Stride;
+                else if (c < n_x_pre + n_h) a_base = h_base + (c - n_x_pre) * 4 * kK8Stride;
+                else if (c < nchunks) a_base = x_base + (c - n_x_pre - n_h) * 4 * kK8Stride;
+                else a_base = x_base + bias_a_off;   // bias chunk: 16 channels ending in the constant 1
+                const uint32_t b_base = tc::smem_u32(w_buf + s * kStage2Bytes);
+                const int nk = c < nchunks ? 2 : 1;
+                if (tc::elect_one()) {
+#pragma unroll
+                  for (int kk = 0; kk < 2; ++kk) {
+                    if (kk < nk && !(dbg & 2)) {
+                      const uint64_t da = tc::make_smem_desc(a_base + kk * 2 * kK8Stride, kK8Stride, 128);
+                      const uint64_t db = tc::make_smem_desc(b_base + kk * 2 * b_lbo, b_lbo, 128);
+                      tc::mma2_bf16_ss(tmem + ph * CTX_MLP_W, da, db, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+                    }
+                  }
+                  if (c == ntot - 1) tc::mma2_commit(&ctl->acc_full[ph]);
+                  if (g & 1) tc::mma2_commit(&ctl->empty[pr]);
+                }
+                __syncwarp();
+                t_issue += PCLK() - w0;
+              }
+            }
+          }
+        }
+        if (kProf && a.prof && lane == 0) {
+          unsigned long long* pp = a.prof + blockIdx.x * 16;
+          pp[2] = t_act; pp[3] = t_full; pp[4] = t_peer; pp[9] = t_issue; pp[5] = PCLK() - t_begin; pp[14] = t_ldc;
         }
       }
     }
   } else {
-    // ===================== encode + epilogue warps =====================
-    const int t = (warp - 2) >> 2;            // tile handled by this warp
-    const int q = warp & 3;                   // TMEM lane quarter this warp may access
+    // ============ encode + epilogue warps ============
+    const int q = warp & 3;                 // TMEM lane quarter
+    const int hi = (warp - 2) >> 2;         // epilogue: column half ; encode: tile (0 = A, 1 = B)
     const int row = q * 32 + lane;
-    uint8_t* my_h = h_buf + t * kHBytes;
-    uint8_t* my_x = x_buf + t * kXBytes;
-    const uint32_t my_acc = tmem + t * CTX_MLP_W + ((uint32_t)(q * 32) << 16);
     const float* fp = a.fparams;
-    uint32_t acc_phase = 0;
-    const bool has_views = net.in_views > 0;
+    // head weights: shared memory for the view-direction net, global (L2) for the 4 x 256 output_linear
+    const float* hw = net.in_views > 0 ? s_head : a.fparams + net.head_off;
+    uint32_t acc_phase[2] = {0, 0};
+    float alpha_part[2] = {0.f, 0.f};
+    uint8_t* const acts_base = a.acts;
+    const int act_tile_bytes = net.act_tile_bytes, dbg = a.debug;
+    const int64_t nP = a.P;
+    long long t_acc = 0, t_body = 0, t_enc = 0;
+    const long long t_begin = PCLK();
 
-    for (int64_t it = blockIdx.x; it < n_iters_total; it += gridDim.x) {
-      const int64_t tile_idx = it * kTiles + t;
+    auto arrive_act = [&](int ph) {
+      tc::fence_proxy_async_smem();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (r == 0) tc::mbar_arrive(&ctl->act_ready[ph]);
+        else tc::mbar_arrive_remote(&ctl->act_ready[ph], 0);
+      }
+    };
+    auto encode_tile = [&](int64_t it, int te) {   // encode rows of tile `te` for cluster iteration `it`
+      const int64_t tile_idx = it * 4 + te * 2 + r;
       const int64_t p = tile_idx * kTileM + row;
       const bool valid = p < a.P;
       uint8_t* rec = a.acts ? a.acts + (size_t)tile_idx * net.act_tile_bytes : nullptr;
-      float dirs[3] = {0.f, 0.f, 0.f};
-      // ---- encode the point into the layer-0 A operand ----
+      uint8_t* my_x = x_buf + te * kXBytes;
       if (a.mode == 1) {
         float xyz[3] = {0.f, 0.f, 0.f};
         if (valid) {
-          const int64_t r = p / a.S;
+          const int64_t ry = p / a.S;
           const float zv = a.z[p];
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            xyz[j] = a.rays_o[r * 3 + j] + a.rays_d[r * 3 + j] * zv;
-            if (has_views) dirs[j] = a.viewdirs[r * 3 + j];
-          }
+          for (int j = 0; j < 3; ++j) xyz[j] = a.rays_o[ry * 3 + j] + a.rays_d[ry * 3 + j] * zv;
         }
-        encode_row<CTX_MLP_XP_PAD, 10>(my_x, row, xyz, a.L_pts, valid, rec ? rec + net.xp_slot : nullptr);
+        encode_row2<CTX_MLP_XP_PAD, 10>(my_x, row, xyz, a.L_pts, valid, rec ? rec + net.xp_slot : nullptr);
       } else {
         float v[CTX_MLP_XP_PAD];
 #pragma unroll
-        for (int i = 0; i < CTX_MLP_XP_PAD; ++i)
-          v[i] = (valid && i < net.in_pts) ? __ldg(a.x + p * a.x_ld + i) : 0.f;
+        for (int i = 0; i < CTX_MLP_XP_PAD; ++i) v[i] = (valid && i < net.in_pts) ? __ldg(a.x + p * a.x_ld + i) : 0.f;
+        v[CTX_MLP_XP_PAD - 1] = 1.0f;
 #pragma unroll
         for (int c0 = 0; c0 < CTX_MLP_XP_PAD; c0 += 8)
-          store_row8(my_x, row, c0, v + c0, false, rec ? rec + net.xp_slot : nullptr);
+          store_row8(my_x, row, c0, v + c0, false, rec ? rec + net.xp_slot : nullptr, CTX_MLP_XP_PAD);
       }
-      tc::fence_proxy_async_smem();
-      tc::mbar_arrive(&ctl->act_ready[t]);
+    };
 
-      float alpha = 0.f;
+    // prologue: both tiles of the first iteration
+    if (cid < n_citers) encode_tile(cid, hi);
+    arrive_act(0);
+    arrive_act(1);
+
+    for (int64_t it = cid; it < n_citers; it += ncl) {
       for (int l = 0; l < net.n_layers; ++l) {
-        const CtxMlpLayer& L = net.L[l];
-        tc::mbar_wait(&ctl->acc_full[t], acc_phase);
-        acc_phase ^= 1;
-        tc::tc_fence_after();
-        const bool is_final = (L.epi == CTX_EPI_FINAL_VIEWS || L.epi == CTX_EPI_FINAL_OUT);
-        const bool write_h = !is_final || rec != nullptr;
-        float head[4] = {0.f, 0.f, 0.f, 0.f};
-        const float* hw = fp + net.head_off;
-        for (int cb = 0; cb < L.N / 32; ++cb) {
-          uint32_t vr[32];
-          tc::tmem_ld32(my_acc + cb * 32, vr);
-          const float4* b4 = reinterpret_cast<const float4*>(fp + L.bias_off + cb * 32);
-          float bias[32];
+        const int Lepi = net.L[l].epi, LN = net.L[l].N, Lrelu = net.L[l].relu;
+        const int Lmask = net.L[l].mask_slot, Lact = net.L[l].act_slot;
+        const bool is_final = (Lepi == CTX_EPI_FINAL_VIEWS || Lepi == CTX_EPI_FINAL_OUT);
+        const int ncb = LN / 64;            // 32-column blocks handled by this warp (its half of N)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(b4 + j);
-            bias[4 * j] = b.x; bias[4 * j + 1] = b.y; bias[4 * j + 2] = b.z; bias[4 * j + 3] = b.w;
-          }
-          tc::tmem_wait_ld();
-          float v[32];
-          uint32_t neg = 0;   // bit (31-j) = sign of pre-activation j (the ReLU mask the dgrad kernel reads)
+        for (int ph = 0; ph < 2; ++ph) {
+          const int64_t tile_idx = it * 4 + ph * 2 + r;
+          const int64_t p = tile_idx * kTileM + row;
+          const bool valid = p < nP;
+          uint8_t* rec = acts_base ? acts_base + (size_t)tile_idx * act_tile_bytes : nullptr;
+          uint8_t* my_h = h_buf + ph * kHBytes;
+          uint8_t* my_x = x_buf + ph * kXBytes;
+          const uint32_t my_acc = tmem + ph * CTX_MLP_W + ((uint32_t)(q * 32) << 16);
+          const long long e0 = PCLK();
+          tc::mbar_wait(&ctl->acc_full[ph], acc_phase[ph]);
+          const long long e1 = PCLK();
+          t_acc += e1 - e0;
+          acc_phase[ph] ^= 1;
+          tc::tc_fence_after();
+          float head[4] = {0.f, 0.f, 0.f, 0.f};
+          // The bias is already inside the accumulator (constant-1 channel x bias row of the weight stream),
+          // so a hidden-layer epilogue is: TMEM load -> (training: sign mask) -> relu+bf16 pack -> store.
+          auto process = [&](const uint32_t (&vr)[32], int cb) {
+            if (rec && Lmask >= 0) {
+              uint32_t neg = 0;   // bit (31-j) = sign of pre-activation j (the ReLU mask the dgrad kernel reads)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            v[j] = __uint_as_float(vr[j]) + bias[j];
-            if (rec) neg = __funnelshift_l(__float_as_uint(v[j]), neg, 1);
-            if (L.relu) v[j] = fmaxf(v[j], 0.f);
-          }
-          if (rec && L.mask_slot >= 0)
-            reinterpret_cast<uint32_t*>(rec + L.mask_slot)[row * (L.N / 32) + cb] = neg;
-          if (L.epi == CTX_EPI_HIDDEN_ALPHA) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) alpha = fmaf(bf16_round(v[j]), __ldg(hw + cb * 32 + j), alpha);
-          } else if (L.epi == CTX_EPI_FINAL_VIEWS) {
-            const float* wr = hw + 260;  // W_rgb [3][128]
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float hv = bf16_round(v[j]);
-              head[0] = fmaf(hv, __ldg(wr + cb * 32 + j), head[0]);
-              head[1] = fmaf(hv, __ldg(wr + 128 + cb * 32 + j), head[1]);
-              head[2] = fmaf(hv, __ldg(wr + 256 + cb * 32 + j), head[2]);
+              for (int j = 0; j < 32; ++j) neg = __funnelshift_l(vr[j], neg, 1);
+              reinterpret_cast<uint32_t*>(rec + Lmask)[row * (LN / 32) + cb] = neg;
             }
-          } else if (L.epi == CTX_EPI_FINAL_OUT) {
+            float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float hv = bf16_round(v[j]);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(vr[j]);
+            if (Lepi == CTX_EPI_HIDDEN_ALPHA) {
+              float acc = alpha_part[ph];
 #pragma unroll
-              for (int o = 0; o < 4; ++o) head[o] = fmaf(hv, __ldg(hw + o * 256 + cb * 32 + j), head[o]);
+              for (int j = 0; j < 32; ++j) acc = fmaf(bf16_round(fmaxf(v[j], 0.f)), hw[cb * 32 + j], acc);
+              alpha_part[ph] = acc;
+            } else if (Lepi == CTX_EPI_FINAL_VIEWS) {
+              const float* wr = hw + 260;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float hv = bf16_round(fmaxf(v[j], 0.f));
+                head[0] = fmaf(hv, wr[cb * 32 + j], head[0]);
+                head[1] = fmaf(hv, wr[128 + cb * 32 + j], head[1]);
+                head[2] = fmaf(hv, wr[256 + cb * 32 + j], head[2]);
+              }
+            } else if (Lepi == CTX_EPI_FINAL_OUT) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float hv = bf16_round(fmaxf(v[j], 0.f));
+#pragma unroll
+                for (int o = 0; o < 4; ++o) head[o] = fmaf(hv, hw[o * 256 + cb * 32 + j], head[o]);
+              }
+            }
+            if (!is_final || rec) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8)
+                store_row8(is_final ? nullptr : my_h, row, cb * 32 + j, v + j, Lrelu != 0,
+                           rec ? rec + Lact : nullptr, LN);
+            }
+          };
+          if (!(dbg & 1)) {
+            uint32_t va[32], vb[32];
+            const int cb0 = hi * ncb;
+            tc::tmem_ld32(my_acc + cb0 * 32, va);
+            for (int cbi = 0; cbi < ncb; cbi += 2) {     // ncb is 2 or 4; loads run one block ahead
+              tc::tmem_wait_ld();
+              tc::tmem_ld32(my_acc + (cb0 + cbi + 1) * 32, vb);
+              process(va, cb0 + cbi);
+              tc::tmem_wait_ld();
+              if (cbi + 2 < ncb) tc::tmem_ld32(my_acc + (cb0 + cbi + 2) * 32, va);
+              process(vb, cb0 + cbi + 1);
             }
           }
-          if (write_h) {
+          if (Lepi == CTX_EPI_HIDDEN_ALPHA && hi == 0) {
+            // the point encoding of this tile is dead: its x buffer now takes the view-direction encoding
+            if (a.mode == 1) {
+              float dirs[3] = {0.f, 0.f, 0.f};
+              if (valid) {
+                const int64_t ry = p / a.S;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              store_row8(is_final ? nullptr : my_h, row, cb * 32 + j, v + j, false, rec ? rec + L.act_slot : nullptr);
-          }
-        }
-        if (L.epi == CTX_EPI_HIDDEN_ALPHA) {
-          alpha += __ldg(hw + 256);
-          // the point encoding is dead from here on: encode the view direction into the x buffer
-          if (a.mode == 1) {
-            encode_row<CTX_MLP_XD_PAD, 4>(my_x, row, dirs, a.L_dirs, valid, rec ? rec + net.xd_slot : nullptr);
-          } else {
-            float vv[CTX_MLP_XD_PAD];
-#pragma unroll
-            for (int i = 0; i < CTX_MLP_XD_PAD; ++i)
-              vv[i] = (valid && i < net.in_views) ? __ldg(a.x + p * a.x_ld + net.in_pts + i) : 0.f;
-#pragma unroll
-            for (int c0 = 0; c0 < CTX_MLP_XD_PAD; c0 += 8)
-              store_row8(my_x, row, c0, vv + c0, false, rec ? rec + net.xd_slot : nullptr);
-          }
-        }
-        if (is_final) {
-          if (valid) {
-            if (L.epi == CTX_EPI_FINAL_VIEWS) {
-              const float* br = hw + 260 + 384;
-              float4 o4 = make_float4(head[0] + __ldg(br), head[1] + __ldg(br + 1), head[2] + __ldg(br + 2), alpha);
-              *reinterpret_cast<float4*>(a.out + p * 4) = o4;
+                for (int j = 0; j < 3; ++j) dirs[j] = a.viewdirs[ry * 3 + j];
+              }
+              encode_row2<CTX_MLP_XD_PAD, 4>(my_x, row, dirs, a.L_dirs, valid, rec ? rec + net.xd_slot : nullptr);
             } else {
-              const float* bo = hw + 1024;
+              float vv[CTX_MLP_XD_PAD];
 #pragma unroll
-              for (int o = 0; o < 4; ++o)
-                if (o < net.out_ch) a.out[p * net.out_ch + o] = head[o] + __ldg(bo + o);
+              for (int i = 0; i < CTX_MLP_XD_PAD; ++i)
+                vv[i] = (valid && i < net.in_views) ? __ldg(a.x + p * a.x_ld + net.in_pts + i) : 0.f;
+              vv[CTX_MLP_XD_PAD - 1] = 1.0f;
+#pragma unroll
+              for (int c0 = 0; c0 < CTX_MLP_XD_PAD; c0 += 8)
+                store_row8(my_x, row, c0, vv + c0, false, rec ? rec + net.xd_slot : nullptr, CTX_MLP_XD_PAD);
             }
           }
+          if (is_final) {
+            // the two column halves add their partial head sums into the zero-initialised output
+            if (valid) {
+              if (Lepi == CTX_EPI_FINAL_VIEWS) {
+                const float* br = hw + 260 + 384;
+                float* o4 = a.out + p * 4;
+                atomicAdd(o4 + 0, head[0] + (hi == 0 ? br[0] : 0.f));
+                atomicAdd(o4 + 1, head[1] + (hi == 0 ? br[1] : 0.f));
+                atomicAdd(o4 + 2, head[2] + (hi == 0 ? br[2] : 0.f));
+                atomicAdd(o4 + 3, alpha_part[ph] + (hi == 0 ? hw[256] : 0.f));
+              } else {
+                const float* bo = hw + 1024;
+#pragma unroll
+                for (int o = 0; o < 4; ++o)
+                  if (o < net.out_ch) atomicAdd(a.out + p * net.out_ch + o, head[o] + (hi == 0 ? bo[o] : 0.f));
+              }
+            }
+            alpha_part[ph] = 0.f;
+            // next iteration's point encoding of this tile can start as soon as its last MMAs are done
+            const int64_t nit = it + ncl;
+            const long long e2 = PCLK();
+            if (nit < n_citers && hi == ph) encode_tile(nit, ph);
+            t_enc += PCLK() - e2;
+            if (nit < n_citers) arrive_act(ph);
+          } else {
+            arrive_act(ph);
+          }
+          t_body += PCLK() - e1;
         }
-        if (!is_final) tc::fence_proxy_async_smem();
-        tc::tc_fence_before();
-        if (!is_final) tc::mbar_arrive(&ctl->act_ready[t]);
       }
+    }
+    if (kProf && a.prof && lane == 0 && (warp == 2 || warp == 9)) {
+      unsigned long long* pp = a.prof + blockIdx.x * 16 + (warp == 2 ? 6 : 10);
+      pp[0] = t_acc; pp[1] = t_body; pp[2] = PCLK() - t_begin;
+      if (warp == 2) a.prof[blockIdx.x * 16 + 13] = t_enc;
     }
   }
 
   tc::tc_fence_before();
-  __syncthreads();
+  tc::cluster_sync_all();
   if (warp == 1) {
     __syncwarp();
-    tc::tmem_dealloc(tmem, 512);
+    tc::tmem_dealloc2(tmem, 512);
   }
+#undef PCLK
 }
 
 }  // namespace ctx
 
+// diagnostics: if set (device pointer, 16 x uint64 per CTA), the 2-CTA kernels record where their roles wait
+static void* ctx_mlp_prof_buffer = nullptr;
+static int ctx_mlp_debug_flags = 0;
+extern "C" int ctx_mlp_set_debug(int f) { ctx_mlp_debug_flags = f; return 0; }
+extern "C" int ctx_mlp_set_prof_buffer(void* p) { ctx_mlp_prof_buffer = p; return 0; }
+
 extern "C" int ctx_mlp_fwd(const void* net_host, const void* wpacked, const float* fparams, int mode,
-                           const float* x, int x_ld, const float* rays_o, const float* rays_d,
-                           const float* viewdirs, const float* z, int S, int L_pts, int L_dirs, int64_t P,
-                           float* out, void* acts, void* stream) {
+                            const float* x, int x_ld, const float* rays_o, const float* rays_d,
+                            const float* viewdirs, const float* z, int S, int L_pts, int L_dirs, int64_t P,
+                            float* out, void* acts, void* stream) {
   if (!net_host || !wpacked || !fparams || !out || P < 0) return CTX_ERR_BAD_ARG;
   if (P == 0) return 0;
   ctx::MlpFwdArgs a;
@@ -306,16 +447,24 @@ extern "C" int ctx_mlp_fwd(const void* net_host, const void* wpacked, const floa
   }
   a.wpacked = (const uint8_t*)wpacked; a.fparams = fparams; a.mode = mode; a.x = x; a.x_ld = x_ld;
   a.rays_o = rays_o; a.rays_d = rays_d; a.viewdirs = viewdirs; a.z = z; a.S = S; a.L_pts = L_pts;
-  a.L_dirs = L_dirs; a.P = P; a.out = out; a.acts = (uint8_t*)acts; a.prof = nullptr; a.debug = 0;
+  a.L_dirs = L_dirs; a.P = P; a.out = out; a.acts = (uint8_t*)acts;
+  a.prof = (unsigned long long*)ctx_mlp_prof_buffer; a.debug = ctx_mlp_debug_flags;
+  cudaStream_t st = (cudaStream_t)stream;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(ctx::mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)ctx::kMlpSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(ctx::mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)ctx::kMlp2SmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(ctx::mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)ctx::kMlp2SmemBytes);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
-  const int64_t iters = ctx::ceil_div(P, (int64_t)ctx::kTileM * ctx::kTiles);
-  const int grid = (int)(iters < ctx::kNumSMs ? iters : ctx::kNumSMs);
-  ctx::mlp_fwd_kernel<<<grid, ctx::kMlpThreads, ctx::kMlpSmemBytes, (cudaStream_t)stream>>>(a);
+  cudaError_t e = cudaMemsetAsync(out, 0, (size_t)P * a.net.out_ch * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  const int64_t citers = ctx::ceil_div(P, (int64_t)ctx::kTileM * 4);
+  const int ncl = (int)(citers < ctx::kNumSMs / 2 ? citers : ctx::kNumSMs / 2);
+  if (a.prof) ctx::mlp_fwd_kernel<true><<<2 * ncl, ctx::kMlpThreads, ctx::kMlp2SmemBytes, st>>>(a);
+  else ctx::mlp_fwd_kernel<false><<<2 * ncl, ctx::kMlpThreads, ctx::kMlp2SmemBytes, st>>>(a);
   CTX_RETURN_LAST();
 }

@@ -5,9 +5,10 @@
 // in_views > 0, the upstream view-direction variant (commented :86-95).
 // ctx_mlp_pack converts the fp32 nn.Linear weights ([out,in] row-major, parameter
 // order of :81-97) into (a) the bf16 forward stream: per layer, per 32-wide K
-// chunk, the B operand image [k8][N][8] (canonical no-swizzle K-major layout),
-// (b) the transposed stream used by the dgrad kernel, (c) the fp32 block of
-// biases and head weights.  It runs once per optimizer step (2 x 1.2 MB).
+// chunk, the B operand image [half][k8][N/2][8] (canonical no-swizzle K-major
+// layout; each CTA of an MMA pair stages one half), with the bias riding on the
+// constant-1 input channel, (b) the transposed stream used by the dgrad kernel,
+// (c) the fp32 block of biases and head weights.  Runs once per optimizer step.
 #include "ctx_common.cuh"
 #include "mlp_desc.h"
 #include <string.h>
@@ -29,7 +30,6 @@ struct PackArgs {
   int n_layers;
   PackLayer L[CTX_MLP_MAX_LAYERS];
   uint16_t* w; uint16_t* wt; float* fparams;
-  int w_bytes, wt_bytes;   // each stream buffer holds two copies: [0,bytes) whole-N chunks, [bytes,2*bytes) half-split
   // heads
   int has_views, out_ch, head_off;
   const float* w_alpha; const float* b_alpha; const float* w_rgb; const float* b_rgb;
@@ -75,15 +75,14 @@ __global__ void mlp_pack_kernel(const __grid_constant__ PackArgs a) {
       k -= L.seg[s].pad;
     }
     uint16_t val = (col >= 0 && n < L.out_rows) ? f2bf(L.W[(size_t)n * L.ld + col]) : (uint16_t)0;
-    dst[e] = val;
     if (one_channel && !L.bias_mma && n < L.out_rows) val = f2bf(L.b[n]);   // bias rides on the constant-1 channel
-    // half-split copy for the 2-CTA kernels: chunk = [half][k8][N/2][8]
+    // half-split chunk for the 2-CTA MMAs: [half][k8][N/2][8] (each CTA of the pair stages one half)
     const int Nh = L.N >> 1, hf = n / Nh, nl = n - hf * Nh;
-    a.w[(a.w_bytes + L.w_off) / 2 + c * (L.N * 32) + hf * (Nh * 32) + k8 * (Nh * 8) + nl * 8 + kk] = val;
+    dst[c * (L.N * 32) + hf * (Nh * 32) + k8 * (Nh * 8) + nl * 8 + kk] = val;
   }
   for (int i = tid; i < L.N; i += nth) a.fparams[L.bias_off + i] = i < L.out_rows ? L.b[i] : 0.f;
   if (L.bias_mma) {   // [half][2 k8][N/2][8]: bias at k = 15 (the constant-1 channel), zeros elsewhere
-    uint16_t* bc = a.w + (a.w_bytes + L.w_off) / 2 + Kpad * L.N;
+    uint16_t* bc = a.w + L.w_off / 2 + Kpad * L.N;
     const int Nh = L.N >> 1;
     for (int e = tid; e < 16 * L.N; e += nth) {
       const int hf = e / (16 * Nh), r0 = e - hf * 16 * Nh;
@@ -102,9 +101,8 @@ __global__ void mlp_pack_kernel(const __grid_constant__ PackArgs a) {
       const int n = r1 >> 3, kk = r1 & 7;
       const int k = c * 32 + k8 * 8 + kk;  // output feature
       const uint16_t val = (k < L.out_rows) ? f2bf(L.W[(size_t)k * L.ld + L.h_src + n]) : (uint16_t)0;
-      dt[e] = val;
       const int hf = n >> 7, nl = n & 127;
-      a.wt[(a.wt_bytes + L.wt_off) / 2 + c * (256 * 32) + hf * (128 * 32) + k8 * (128 * 8) + nl * 8 + kk] = val;
+      dt[c * (256 * 32) + hf * (128 * 32) + k8 * (128 * 8) + nl * 8 + kk] = val;
     }
   }
 }
@@ -192,7 +190,6 @@ extern "C" int ctx_mlp_pack(const void* net_host, const float* const* params, in
   memset(&a, 0, sizeof(a));
   a.n_layers = net.n_layers; a.w = (uint16_t*)wpacked; a.wt = (uint16_t*)wtpacked; a.fparams = fparams;
   a.has_views = views; a.out_ch = net.out_ch; a.head_off = net.head_off;
-  a.w_bytes = net.w_bytes; a.wt_bytes = net.wt_bytes;
   for (int l = 0; l < net.n_layers; ++l) {
     const CtxMlpLayer& L = net.L[l];
     ctx::PackLayer& P = a.L[l];

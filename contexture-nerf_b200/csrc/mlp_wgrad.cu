@@ -1,0 +1,334 @@
+// Weight gradients of the coordinate MLP on tcgen05 / TMEM, and the ctx_mlp_bwd entry point.
+//
+//   dgrad (mlp_dgrad.cu) leaves dZ of every GEMM layer in the dZ records; the forward left the layer
+//   inputs in the activation records.  wgrad: dW = dZ^T * A summed over all points -- a split-K GEMM whose
+//   K dimension is the point index.  Both operands are [points x features] tile images consumed as
+//   MN-major operands, so no transposition pass exists anywhere.  Each CTA owns one (layer, segment) job
+//   and a slice of the point tiles, accumulates in TMEM, and flushes with fp32 red.global.add into the
+//   flat gradient bucket; bias gradients are column sums of dZ taken from the shared-memory tile while
+//   the MMAs run.  The kernel is HBM-bound (1 KB read per point per layer).
+//
+// Gradients flow to the parameters only (the encoded inputs are data).
+// Reference semantics: autograd through NeRF2D.forward,
+// /root/reference/src/run_nerf_helpers.py:106-135.
+#include "mlp_common.cuh"
+#include <string.h>
+#include <stdlib.h>
+
+// dgrad kernel launcher (mlp_dgrad.cu)
+int ctx_launch_dgrad(const CtxMlpNet& net, const void* wtpacked, const float* fparams, const float* g_out,
+                      const void* acts, void* dacts, int64_t P, cudaStream_t st);
+
+namespace ctx {
+
+// ============================== wgrad ======================================
+// Units of the operand ring are HALF tiles (64 points x channels, <= 32 KB, contiguous in the record);
+// a group = {A half, B half} feeds 4 K16 MMAs per 128-wide M half.  Six 32 KB slots = three groups: one
+// being consumed, two in flight from HBM, which is what it takes to keep the per-SM share of the HBM
+// bandwidth busy (the kernel is bandwidth-bound: 1 KB per point per layer).
+constexpr int kWgUnitBytes = 32768;
+constexpr int kWgUnits = 6;
+constexpr int kWgThreads = 192;     // warp 0 producer, warp 1 MMA, warps 2-5 column sums + flush
+constexpr int kWgMaxJobs = 48;
+constexpr size_t kWgSmemBytes = (size_t)kWgUnits * kWgUnitBytes + 256;
+
+struct WgJob {
+  int a_slot, a_ch, a_dz;       // A operand tile: record offset, channels (M, multiple of 128), from dZ records?
+  int b_slot, b_ch, b_dz;       // B operand tile: channels = N (multiple of 16)
+  float* out; int ld_out; int col_off;
+  int transposed;               // 1: out[(n-n_lo)*ld + col_off + m]   0: out[m*ld + col_off + (n-n_lo)]
+  int m_valid, n_lo, n_hi;
+  float* bias_out; int bias_from_b; int bias_lo, bias_hi;   // column sums of the dZ operand -> bias_out[c - bias_lo]
+  int cta_begin, cta_count;
+};
+struct WgradArgs {
+  int n_jobs;
+  WgJob job[kWgMaxJobs];
+  const uint8_t* acts; const uint8_t* dacts;
+  int tile_bytes;
+  int64_t n_tiles;
+};
+struct __align__(8) WgCtl {
+  uint64_t full[kWgUnits], empty[kWgUnits], done;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const __grid_constant__ WgradArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  WgCtl* ctl = reinterpret_cast<WgCtl*>(smem + kWgUnits * kWgUnitBytes);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // which job does this CTA serve?
+  int ji = 0;
+  for (int j = 0; j < a.n_jobs; ++j)
+    if ((int)blockIdx.x >= a.job[j].cta_begin && (int)blockIdx.x < a.job[j].cta_begin + a.job[j].cta_count) ji = j;
+  const WgJob& J = a.job[ji];
+  const int split = blockIdx.x - J.cta_begin, cta_count = J.cta_count;
+  const int a_ch = J.a_ch, b_ch = J.b_ch;
+  const int m_halves = a_ch / 128;
+  const uint32_t a_bytes = 64u * a_ch * 2, b_bytes = 64u * b_ch * 2;   // one 64-point half of each operand
+  int64_t my_tiles = 0;
+  if (split < a.n_tiles) my_tiles = (a.n_tiles - split + cta_count - 1) / cta_count;
+  const int64_t my_groups = 2 * my_tiles;
+
+  if (tid == 0) {
+    for (int s = 0; s < kWgUnits; ++s) { tc::mbar_init(&ctl->full[s], 1); tc::mbar_init(&ctl->empty[s], 5); }
+    tc::mbar_init(&ctl->done, 1);
+    tc::mbar_fence_init();
+  }
+  if (warp == 1) tc::tmem_alloc(&ctl->tmem_base, 512);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = ctl->tmem_base;
+
+  if (warp == 0) {
+    const uint8_t* a_src = (J.a_dz ? a.dacts : a.acts) + J.a_slot;
+    const uint8_t* b_src = (J.b_dz ? a.dacts : a.acts) + J.b_slot;
+    const size_t tile_bytes = a.tile_bytes;
+    uint32_t u = 0;
+    for (int64_t gi = 0; gi < my_groups; ++gi) {
+      const int64_t tile = split + (gi >> 1) * cta_count;
+      const size_t base = (size_t)tile * tile_bytes;
+      const int hf = (int)(gi & 1);
+      for (int which = 0; which < 2; ++which, ++u) {
+        const int s = u % kWgUnits;
+        tc::mbar_wait(&ctl->empty[s], ((u / kWgUnits) & 1) ^ 1);
+        if (tc::elect_one()) {
+          const uint8_t* src = which == 0 ? a_src + base + (size_t)hf * a_bytes : b_src + base + (size_t)hf * b_bytes;
+          const uint32_t bytes = which == 0 ? a_bytes : b_bytes;
+          tc::mbar_arrive_expect_tx(&ctl->full[s], bytes);
+          tc::bulk_g2s(smem + s * kWgUnitBytes, src, bytes, &ctl->full[s]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = tc::make_idesc_bf16(128, b_ch, 1, 1);
+    uint32_t u = 0;
+    for (int64_t gi = 0; gi < my_groups; ++gi, u += 2) {
+      const int sa = u % kWgUnits, sb = (u + 1) % kWgUnits;
+      tc::mbar_wait(&ctl->full[sa], (u / kWgUnits) & 1);
+      tc::mbar_wait(&ctl->full[sb], ((u + 1) / kWgUnits) & 1);
+      tc::tc_fence_after();
+      const uint32_t a_base = tc::smem_u32(smem + sa * kWgUnitBytes);
+      const uint32_t b_base = tc::smem_u32(smem + sb * kWgUnitBytes);
+      if (tc::elect_one()) {
+        for (int mh = 0; mh < m_halves; ++mh) {
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) {
+            // MN-major half tile: SBO = 1024 (next 8 channels), LBO = 128 (next 8 points); 16 points = 256 B
+            const uint64_t da = tc::make_smem_desc(a_base + mh * 16 * 1024 + k16 * 256, 128, 1024);
+            const uint64_t db = tc::make_smem_desc(b_base + k16 * 256, 128, 1024);
+            tc::mma_bf16_ss(tmem + mh * 256, da, db, idesc, (gi > 0 || k16 > 0) ? 1u : 0u);
+          }
+        }
+        tc::mma_commit(&ctl->empty[sa]);
+        tc::mma_commit(&ctl->empty[sb]);
+        if (gi == my_groups - 1) tc::mma_commit(&ctl->done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---- column sums of the dZ operand (bias gradients), then the flush ----
+    const int cw = warp - 2;  // 0..3
+    const bool do_bias = J.bias_out != nullptr;
+    const int bias_from_b = J.bias_from_b;
+    const int dz_ch = bias_from_b ? b_ch : a_ch;
+    const int n_chunks = dz_ch / 8;
+    float s_lo[8], s_hi[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s_lo[i] = 0.f; s_hi[i] = 0.f; }
+    uint32_t u = 0;
+    for (int64_t gi = 0; gi < my_groups; ++gi, u += 2) {
+      const int sa = u % kWgUnits, sb = (u + 1) % kWgUnits;
+      // always wait for both units: keeps these warps within one ring phase of the MMA issuer
+      tc::mbar_wait(&ctl->full[sa], (u / kWgUnits) & 1);
+      tc::mbar_wait(&ctl->full[sb], ((u + 1) / kWgUnits) & 1);
+      if (do_bias) {
+        const uint8_t* tile = smem + (bias_from_b ? sb : sa) * kWgUnitBytes;
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) {
+          const int c = cw + ci * 4;
+          if (c < n_chunks) {
+#pragma unroll
+            for (int gp = 0; gp < 8; ++gp) {
+              const uint32_t w2 = *reinterpret_cast<const uint32_t*>(tile + c * 1024 + gp * 128 + lane * 4);
+              s_lo[ci] += __uint_as_float(w2 << 16);
+              s_hi[ci] += __uint_as_float(w2 & 0xffff0000u);
+            }
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) { tc::mbar_arrive(&ctl->empty[sa]); tc::mbar_arrive(&ctl->empty[sb]); }
+    }
+    if (do_bias) {
+#pragma unroll
+      for (int ci = 0; ci < 8; ++ci) {
+        float lo = s_lo[ci], hi = s_hi[ci];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          lo += __shfl_xor_sync(CTX_FULL_MASK, lo, o);
+          hi += __shfl_xor_sync(CTX_FULL_MASK, hi, o);
+        }
+        const int c = cw + ci * 4;
+        if (c < n_chunks && lane < 4 && my_tiles > 0) {
+          const int ch = c * 8 + lane * 2;
+          if (ch >= J.bias_lo && ch < J.bias_hi) atomicAdd(J.bias_out + ch - J.bias_lo, lo);
+          if (ch + 1 >= J.bias_lo && ch + 1 < J.bias_hi) atomicAdd(J.bias_out + ch + 1 - J.bias_lo, hi);
+        }
+      }
+    }
+    // ---- flush the TMEM accumulators: warp%4 selects the lane quarter ----
+    if (my_tiles > 0) {
+      tc::mbar_wait(&ctl->done, 0);
+      tc::tc_fence_after();
+      const int q = warp & 3;
+      const int n_lo = J.n_lo, n_hi = J.n_hi, ld_out = J.ld_out, col_off = J.col_off, transposed = J.transposed;
+      float* const outp = J.out;
+      for (int mh = 0; mh < m_halves; ++mh) {
+        const int m = mh * 128 + q * 32 + lane;
+        for (int cb = 0; cb < (b_ch + 31) / 32; ++cb) {
+          uint32_t vr[32];
+          if (b_ch - cb * 32 >= 32) {
+            tc::tmem_ld32(tmem + mh * 256 + cb * 32 + ((uint32_t)(q * 32) << 16), vr);
+          } else {  // N = 16 heads: load 16 columns
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(vr[0]), "=r"(vr[1]), "=r"(vr[2]), "=r"(vr[3]), "=r"(vr[4]), "=r"(vr[5]), "=r"(vr[6]),
+                  "=r"(vr[7]), "=r"(vr[8]), "=r"(vr[9]), "=r"(vr[10]), "=r"(vr[11]), "=r"(vr[12]), "=r"(vr[13]),
+                  "=r"(vr[14]), "=r"(vr[15])
+                : "r"(tmem + mh * 256 + cb * 32 + ((uint32_t)(q * 32) << 16))
+                : "memory");
+#pragma unroll
+            for (int j = 16; j < 32; ++j) vr[j] = 0u;
+          }
+          tc::tmem_wait_ld();
+          if (m < J.m_valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = cb * 32 + j;
+              if (n >= n_lo && n < n_hi) {
+                float* dst = transposed ? (outp + (size_t)(n - n_lo) * ld_out + col_off + m)
+                                        : (outp + (size_t)m * ld_out + col_off + (n - n_lo));
+                atomicAdd(dst, __uint_as_float(vr[j]));
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc::tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace ctx
+
+// grads: HOST array of DEVICE pointers in the order of ctx_mlp_pack's `params`
+// (gradients are ACCUMULATED into them: zero them first for a fresh gradient).
+extern "C" int ctx_mlp_bwd(const void* net_host, const void* wtpacked, const float* fparams,
+                           const float* g_out, const void* acts, void* dacts, int64_t P, float* const* grads,
+                           int n_grads, void* stream) {
+  if (!net_host || !wtpacked || !fparams || !g_out || !acts || !dacts || !grads || P < 0) return CTX_ERR_BAD_ARG;
+  if (P == 0) return 0;
+  const CtxMlpNet& net = *reinterpret_cast<const CtxMlpNet*>(net_host);
+  const bool views = net.in_views > 0;
+  const int D = views ? net.n_layers - 2 : net.n_layers;
+  if (n_grads != 2 * D + (views ? 8 : 2)) return CTX_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(ctx::mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)ctx::kWgSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  // ---------------- dgrad ----------------
+  {
+    const int rc = ctx_launch_dgrad(net, wtpacked, fparams, g_out, acts, dacts, P, st);
+    if (rc != 0) return rc;
+  }
+  // ---------------- wgrad ----------------
+  {
+    ctx::WgradArgs w;
+    memset(&w, 0, sizeof(w));
+    w.acts = (const uint8_t*)acts; w.dacts = (const uint8_t*)dacts; w.tile_bytes = net.act_tile_bytes;
+    const int64_t n_tiles = ctx::ceil_div(P, 128);
+    w.n_tiles = n_tiles;
+    int nj = 0;
+    float cost[ctx::kWgMaxJobs];
+    auto add = [&](int a_slot, int a_ch, int a_dz, int b_slot, int b_ch, int b_dz, float* out, int ld, int col_off,
+                   int transposed, int m_valid, int n_lo, int n_hi, float* bias, int bias_from_b, int blo, int bhi) {
+      ctx::WgJob& J = w.job[nj];
+      J.a_slot = a_slot; J.a_ch = a_ch; J.a_dz = a_dz; J.b_slot = b_slot; J.b_ch = b_ch; J.b_dz = b_dz;
+      J.out = out; J.ld_out = ld; J.col_off = col_off; J.transposed = transposed; J.m_valid = m_valid;
+      J.n_lo = n_lo; J.n_hi = n_hi; J.bias_out = bias; J.bias_from_b = bias_from_b; J.bias_lo = blo; J.bias_hi = bhi;
+      cost[nj] = (float)(a_ch + b_ch);   // HBM bytes per point decide the split, the kernel is bandwidth-bound
+      ++nj;
+    };
+    for (int l = 0; l < net.n_layers; ++l) {
+      const CtxMlpLayer& L = net.L[l];
+      int pi;
+      if (l < D) pi = 2 * l; else if (l == D) pi = 2 * D; else pi = 2 * D + 4;
+      float* gW = grads[pi];
+      float* gb = grads[pi + 1];
+      int ld = 0;
+      if (L.n_x_pre) ld += net.in_pts;
+      const int h_col = ld;
+      if (L.n_h) ld += 256;
+      const int xd_col = ld;
+      if (L.n_x_post) ld += net.in_views;
+      bool bias_done = false;
+      if (L.n_h) {  // h segment: transposed job, A = input activations (M = in), B = dZ (N = out)
+        add(L.in_slot, 256, 0, L.act_slot, L.N, 1, gW, ld, h_col, 1, 256, 0, L.N, gb, 1, 0, L.N);
+        bias_done = true;
+      }
+      if (L.n_x_pre) {  // point-encoding segment: A = dZ (M = out), B = x_p tile (N = 64, 63 real)
+        add(L.act_slot, L.N, 1, net.xp_slot, CTX_MLP_XP_PAD, 0, gW, ld, 0, 0, L.N, 0, net.in_pts,
+            bias_done ? nullptr : gb, 0, 0, L.N);
+        bias_done = true;
+      }
+      if (L.n_x_post) {  // view-encoding segment
+        add(L.act_slot, L.N, 1, net.xd_slot, CTX_MLP_XD_PAD, 0, gW, ld, xd_col, 0, L.N, 0, net.in_views, nullptr, 0,
+            0, 0);
+      }
+    }
+    if (views) {
+      const CtxMlpLayer& H = net.L[D - 1];           // alpha_linear reads h_{D-1}
+      const CtxMlpLayer& V = net.L[net.n_layers - 1];
+      add(H.act_slot, 256, 0, net.gout_slot, 16, 1, grads[2 * D + 2], 256, 0, 1, 256, 3, 4, grads[2 * D + 3], 1, 3, 4);
+      add(V.act_slot, 128, 0, net.gout_slot, 16, 1, grads[2 * D + 6], 128, 0, 1, 128, 0, 3, grads[2 * D + 7], 1, 0, 3);
+    } else {
+      const CtxMlpLayer& H = net.L[D - 1];
+      add(H.act_slot, 256, 0, net.gout_slot, 16, 1, grads[2 * D], 256, 0, 1, 256, 0, net.out_ch, grads[2 * D + 1], 1,
+          0, net.out_ch);
+    }
+    // distribute the 148 CTAs over the jobs proportionally to their HBM traffic
+    float total = 0.f;
+    for (int j = 0; j < nj; ++j) total += cost[j];
+    int budget = ctx::kNumSMs, begin = 0;
+    if (budget < nj) return CTX_ERR_UNSUPPORTED;
+    int given[ctx::kWgMaxJobs];
+    int used = 0;
+    for (int j = 0; j < nj; ++j) {
+      int c = (int)(cost[j] / total * (budget - nj)) + 1;
+      if ((int64_t)c > n_tiles) c = (int)n_tiles;
+      if (c < 1) c = 1;
+      given[j] = c; used += c;
+    }
+    for (int j = 0; used < budget && j < 4 * nj; ++j) {   // hand out the remainder to the big jobs
+      const int k = j % nj;
+      if (cost[k] >= 384.f && (int64_t)given[k] < n_tiles) { ++given[k]; ++used; }
+    }
+    for (int j = 0; j < nj; ++j) { w.job[j].cta_begin = begin; w.job[j].cta_count = given[j]; begin += given[j]; }
+    w.n_jobs = nj;
+    ctx::mlp_wgrad_kernel<<<begin, ctx::kWgThreads, ctx::kWgSmemBytes, st>>>(w);
+  }
+  CTX_RETURN_LAST();
+}

@@ -39,7 +39,6 @@ _SIGNATURES = {
     "ctx_mlp_describe": (c_int, [c_int, ctypes.c_uint32, c_int, c_int, c_int, P]),
     "ctx_mlp_pack": (c_int, [P, P, c_int, P, P, P, P]),
     "ctx_mlp_fwd": (c_int, [P, P, P, c_int, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int64, P, P, P]),
-    "ctx_mlp_fwd2": (c_int, [P, P, P, c_int, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int64, P, P, P]),
     "ctx_mlp_set_prof_buffer": (c_int, [P]),
     "ctx_mlp_set_debug": (c_int, [c_int]),
     "ctx_mlp_bwd": (c_int, [P, P, P, P, P, P, c_int64, P, c_int, P]),
@@ -85,7 +84,7 @@ def check(code: int, what: str) -> None:
 
 
 # kernels launched per ABI call (bench.py reports the total as gpu_launches)
-KERNELS_PER_CALL = {"ctx_mlp_bwd": 2, "ctx_mlp_fwd2": 2}
+KERNELS_PER_CALL = {"ctx_mlp_bwd": 2}
 launch_count = 0
 
 

@@ -69,9 +69,8 @@ class PackedWeights:
                 raise _lib.CtxNerfError("MLP parameters must be contiguous fp32 tensors on one CUDA device "
                                         "(ctxnerf has no CPU path)")
         if ent is None:
-            # two copies of each stream: whole-N chunks (cta_group::1 kernels) + half-split (2-CTA kernels)
-            bufs = (torch.empty(2 * d.w_bytes, dtype=torch.uint8, device=dev),
-                    torch.empty(max(2 * d.wt_bytes, 16), dtype=torch.uint8, device=dev),
+            bufs = (torch.empty(d.w_bytes, dtype=torch.uint8, device=dev),
+                    torch.empty(max(d.wt_bytes, 16), dtype=torch.uint8, device=dev),
                     torch.empty(d.n_fparams, dtype=torch.float32, device=dev))
         else:
             bufs = ent[1]
@@ -83,15 +82,9 @@ class PackedWeights:
         return bufs
 
 
-import os as _os
-
-# "2" = 2-CTA cta_group::2 ping-pong kernels (default), "1" = single-CTA kernels
-KERNEL_VERSION = _os.environ.get("CTXNERF_MLP_KERNEL", "2")
-
-
 def _launch_fwd(desc: NetDesc, w, f, *, x=None, rays=None, P: int, out, acts=None, L_pts=10, L_dirs=4):
     dev = out.device
-    fn = "ctx_mlp_fwd2" if KERNEL_VERSION == "2" else "ctx_mlp_fwd"
+    fn = "ctx_mlp_fwd"
     with torch.cuda.device(dev):
         if x is not None:
             call(fn, desc.p, ptr(w), ptr(f), 0, ptr(x), x.shape[-1], None, None, None, None, 0, 0, 0, P,

@@ -110,7 +110,7 @@ int ctx_mlp_describe(int D, uint32_t skip_mask, int in_pts, int in_views, int ou
 /* params: HOST array of n_params DEVICE pointers (fp32, nn.Linear [out,in]) in
  * module order: pts_linears.{0..D-1}.{weight,bias}, then output_linear.{w,b}
  * or feature_linear, alpha_linear, views_linears.0, rgb_linear {w,b}.
- * wpacked [2*w_bytes], wtpacked [2*wt_bytes] (nullable), fparams [n_fparams]: device
+ * wpacked [w_bytes], wtpacked [wt_bytes] (nullable), fparams [n_fparams]: device
  * buffers sized from the net blob (see contexture-nerf_b200/csrc/mlp_desc.h).   */
 int ctx_mlp_pack(const void* net, const float* const* params, int n_params, void* wpacked,
                  void* wtpacked, float* fparams, void* stream);
@@ -118,20 +118,12 @@ int ctx_mlp_pack(const void* net, const float* const* params, int n_params, void
  * mode 1: the P = R*S points o + d*z (z [R,S]) and the view directions are
  * encoded in-kernel straight into shared memory (Embedder.embed :44-45, L_pts
  * / L_dirs frequencies).  out [P,out_ch] raw network output (no activation,
- * :129).  acts (nullable): activation records for ctx_mlp_bwd.                  */
+ * :129).  acts (nullable): activation records for ctx_mlp_bwd, sized for a
+ * multiple of 4 tiles of 128 points (the kernel works on 512 points per SM pair).*/
 int ctx_mlp_fwd(const void* net, const void* wpacked, const float* fparams, int mode, const float* x,
                 int x_ld, const float* rays_o, const float* rays_d, const float* viewdirs,
                 const float* z, int S, int L_pts, int L_dirs, int64_t P, float* out, void* acts,
                 void* stream);
-
-/* Same contract as ctx_mlp_fwd, executed by the 2-CTA kernel (tcgen05.mma.cta_group::2, M = 256 per
- * SM pair, epilogue of one tile pair overlapped with the MMAs of the other).  Reads the half-split copy
- * of the weight stream that ctx_mlp_pack writes behind the first one (wpacked holds 2*w_bytes); acts, if
- * given, must cover a multiple of 4 tiles of 128 points.                                            */
-int ctx_mlp_fwd2(const void* net, const void* wpacked, const float* fparams, int mode, const float* x,
-                 int x_ld, const float* rays_o, const float* rays_d, const float* viewdirs,
-                 const float* z, int S, int L_pts, int L_dirs, int64_t P, float* out, void* acts,
-                 void* stream);
 
 /* Backward of ctx_mlp_fwd w.r.t. the parameters (hand-written dgrad + wgrad
  * tcgen05 kernels; the encoded inputs are data and get no gradient).  g_out
