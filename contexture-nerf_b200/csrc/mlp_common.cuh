@@ -15,7 +15,8 @@ constexpr int kStageBytes = CTX_MLP_W * CTX_MLP_KC * 2;   // 16 KB
 constexpr int kHBytes = kTileM * CTX_MLP_W * 2;            // 64 KB
 constexpr int kXBytes = kTileM * CTX_MLP_XP_PAD * 2;       // 16 KB
 constexpr int kK8Stride = kTileM * 16;                     // 2048 B between 8-wide K chunks of an A tile
-constexpr int kMlpThreads = 320;
+constexpr int kMlpThreads = 352;   // warp 0 producer, warp 1 MMA issuer (tile pair A) / relay, warps 2-9 epilogue,
+                                   // warp 10 MMA issuer (tile pair B)
 constexpr int kEpiThreadsPerTile = 128;
 
 struct MlpFwdArgs {

@@ -114,17 +114,20 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
           //  constant-bank reload of every field on every chunk)
           const int nchunks = net.L[l].n_x_pre + net.L[l].n_h + net.L[l].n_x_post;
           const int ntot = nchunks + net.L[l].bias_mma;
+          const int npad = (ntot + 1) & ~1;   // phases are padded to whole chunk PAIRS (dummy chunk: no copy)
           const uint32_t half = (uint32_t)net.L[l].N * CTX_MLP_KC;   // (N/2 rows) x 32 K x 2 B
           const uint8_t* lsrc = wstream + net.L[l].w_off;
           for (int ph = 0; ph < 2; ++ph) {
-            for (int c = 0; c < ntot; ++c, ++g) {
+            for (int c = 0; c < npad; ++c, ++g) {
               const int s = g % kStages2, pr = s >> 1;
               // regular chunk: 32 K ; trailing bias chunk (c == nchunks): 16 K
               const uint32_t bytes = c < nchunks ? half : half / 2;
               if (!(g & 1)) tc::mbar_wait(&ctl->empty[pr], ((g / kStages2) & 1) ^ 1);
               if (tc::elect_one()) {
-                tc::mbar_expect_tx(&ctl->full[pr], bytes);
-                tc::bulk_g2s(w_buf + s * kStage2Bytes, lsrc + (size_t)c * 2 * half + r * bytes, bytes, &ctl->full[pr]);
+                if (c < ntot) {
+                  tc::mbar_expect_tx(&ctl->full[pr], bytes);
+                  tc::bulk_g2s(w_buf + s * kStage2Bytes, lsrc + (size_t)c * 2 * half + r * bytes, bytes, &ctl->full[pr]);
+                }
                 if (g & 1) tc::mbar_arrive(&ctl->full[pr]);
               }
               __syncwarp();
@@ -133,14 +136,15 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 10) {
     {
       if (r != 0) {
+        if (warp == 1) {
         // ============ peer CTA: relay "my half landed" to the leader ============
         uint32_t g = 0;
         for (int64_t it = cid; it < n_citers; it += ncl)
           for (int l = 0; l < net.n_layers; ++l) {
-            const int nchunks = net.L[l].n_x_pre + net.L[l].n_h + net.L[l].n_x_post + net.L[l].bias_mma;
+            const int nchunks = (net.L[l].n_x_pre + net.L[l].n_h + net.L[l].n_x_post + net.L[l].bias_mma + 1) & ~1;
             for (int c = 0; c < 2 * nchunks; ++c, ++g) {
               if (g & 1) {   // one relay per chunk pair
                 const int pr = (g % kStages2) >> 1;
@@ -150,77 +154,80 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
               }
             }
           }
+        }
       } else {
-        // ============ leader CTA: MMA issuer for the pair ============
-        // one barrier round trip per PAIR of chunks (4 MMAs): the single issuing thread has to stay
-        // ahead of the tensor pipe (128 cycles per MMA), so per-chunk polling is too expensive
-        uint32_t g = 0, act_phase[2] = {0, 0};
+        // ============ leader CTA: two MMA issuers, warp 1 -> tile pair A, warp 10 -> tile pair B ============
+        // Issuing is single-thread work (~400 cycles of dependent instructions per chunk: barrier polls,
+        // descriptor builds, vector->uniform register moves); one thread cannot keep a 128-cycle-per-MMA
+        // pipe fed, two threads working on alternate phases can.  Phases are padded to whole chunk pairs so
+        // each issuer owns (waits on, commits) complete ring pairs.
+        const int ph = warp == 1 ? 0 : 1;
+        uint32_t gl = 0, act_phase = 0;
         const int dbg = a.debug;
-        long long t_act = 0, t_full = 0, t_peer = 0, t_issue = 0, t_ldc = 0;
+        long long t_act = 0, t_full = 0, t_peer = 0, t_issue = 0;
         const long long t_begin = PCLK();
+        const uint32_t x_base = tc::smem_u32(x_buf + ph * kXBytes), h_base = tc::smem_u32(h_buf + ph * kHBytes);
+        const uint32_t acc = tmem + ph * CTX_MLP_W;
         for (int64_t it = cid; it < n_citers; it += ncl) {
           for (int l = 0; l < net.n_layers; ++l) {
-            const long long c0 = PCLK();
             const int n_x_pre = net.L[l].n_x_pre, n_h = net.L[l].n_h, n_x_post = net.L[l].n_x_post;
             const int bias_mma = net.L[l].bias_mma, bias_a_off = net.L[l].bias_a_off, LN = net.L[l].N;
             const int nchunks = n_x_pre + n_h + n_x_post;
-            if (kProf) { asm volatile("" ::"r"(nchunks + bias_mma + bias_a_off + LN)); t_ldc += PCLK() - c0; }
+            const int ntot = nchunks + bias_mma, npad = (ntot + 1) & ~1;
             const uint32_t idesc = tc::make_idesc_bf16(256, LN, 0, 0);
             const uint32_t b_lbo = (uint32_t)(LN / 2) * 16;
-#pragma unroll
-            for (int ph = 0; ph < 2; ++ph) {
-              long long w0 = PCLK();
-              tc::mbar_wait(&ctl->act_ready[ph], act_phase[ph]);
-              t_act += PCLK() - w0;
-              act_phase[ph] ^= 1;
-              tc::tc_fence_after();
-              const int ntot = nchunks + bias_mma;
-              const uint32_t x_base = tc::smem_u32(x_buf + ph * kXBytes), h_base = tc::smem_u32(h_buf + ph * kHBytes);
-              for (int c = 0; c < ntot; ++c, ++g) {
-                const int s = g % kStages2, pr = s >> 1;
-                if (!(g & 1)) {
-                  const uint32_t par = (g / kStages2) & 1;
-                  w0 = PCLK();
-                  tc::mbar_wait(&ctl->full[pr], par);
-                  const long long w1 = PCLK();
-                  if (!(dbg & 4)) tc::mbar_wait(&ctl->peer_full[pr], par);
-                  const long long w2 = PCLK();
-                  t_full += w1 - w0; t_peer += w2 - w1;
-                  tc::tc_fence_after();
-                }
+            uint32_t g = gl + ph * npad;   // this issuer's first chunk of the layer
+            gl += 2 * npad;
+            long long w0 = PCLK();
+            tc::mbar_wait(&ctl->act_ready[ph], act_phase);
+            t_act += PCLK() - w0;
+            act_phase ^= 1;
+            tc::tc_fence_after();
+            for (int c = 0; c < npad; ++c, ++g) {
+              const int s = g % kStages2, pr = s >> 1;
+              if (!(g & 1)) {
+                const uint32_t par = (g / kStages2) & 1;
                 w0 = PCLK();
-                uint32_t a_base;
-                if (c < n_x_pre) a_base = x_base + c * 4 * kK8Stride;
-                else if (c < n_x_pre + n_h) a_base = h_base + (c - n_x_pre) * 4 * kK8Stride;
-                else if (c < nchunks) a_base = x_base + (c - n_x_pre - n_h) * 4 * kK8Stride;
-                else a_base = x_base + bias_a_off;   // bias chunk: 16 channels ending in the constant 1
-                const uint32_t b_base = tc::smem_u32(w_buf + s * kStage2Bytes);
-                const int nk = c < nchunks ? 2 : 1;
-                if (tc::elect_one()) {
-#pragma unroll
-                  for (int kk = 0; kk < 2; ++kk) {
-                    if (kk < nk && !(dbg & 2)) {
-                      const uint64_t da = tc::make_smem_desc(a_base + kk * 2 * kK8Stride, kK8Stride, 128);
-                      const uint64_t db = tc::make_smem_desc(b_base + kk * 2 * b_lbo, b_lbo, 128);
-                      tc::mma2_bf16_ss(tmem + ph * CTX_MLP_W, da, db, idesc, (c > 0 || kk > 0) ? 1u : 0u);
-                    }
-                  }
-                  if (c == ntot - 1) tc::mma2_commit(&ctl->acc_full[ph]);
-                  if (g & 1) tc::mma2_commit(&ctl->empty[pr]);
-                }
-                __syncwarp();
-                t_issue += PCLK() - w0;
+                tc::mbar_wait(&ctl->full[pr], par);
+                const long long w1 = PCLK();
+                if (!(dbg & 4)) tc::mbar_wait(&ctl->peer_full[pr], par);
+                const long long w2 = PCLK();
+                t_full += w1 - w0; t_peer += w2 - w1;
+                tc::tc_fence_after();
               }
+              w0 = PCLK();
+              uint32_t a_base;
+              if (c < n_x_pre) a_base = x_base + c * 4 * kK8Stride;
+              else if (c < n_x_pre + n_h) a_base = h_base + (c - n_x_pre) * 4 * kK8Stride;
+              else if (c < nchunks) a_base = x_base + (c - n_x_pre - n_h) * 4 * kK8Stride;
+              else a_base = x_base + bias_a_off;   // bias chunk: 16 channels ending in the constant 1
+              const uint32_t b_base = tc::smem_u32(w_buf + s * kStage2Bytes);
+              const int nk = c < nchunks ? 2 : (c < ntot ? 1 : 0);   // regular / bias / dummy chunk
+              if (tc::elect_one()) {
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                  if (kk < nk && !(dbg & 2)) {
+                    const uint64_t da = tc::make_smem_desc(a_base + kk * 2 * kK8Stride, kK8Stride, 128);
+                    const uint64_t db = tc::make_smem_desc(b_base + kk * 2 * b_lbo, b_lbo, 128);
+                    tc::mma2_bf16_ss(acc, da, db, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+                  }
+                }
+                if (c == ntot - 1) tc::mma2_commit(&ctl->acc_full[ph]);
+                if (g & 1) tc::mma2_commit(&ctl->empty[pr]);
+              }
+              __syncwarp();
+              t_issue += PCLK() - w0;
             }
           }
         }
         if (kProf && a.prof && lane == 0) {
-          unsigned long long* pp = a.prof + blockIdx.x * 16;
-          pp[2] = t_act; pp[3] = t_full; pp[4] = t_peer; pp[9] = t_issue; pp[5] = PCLK() - t_begin; pp[14] = t_ldc;
+          unsigned long long* pp = a.prof + blockIdx.x * 16 + (ph ? 0 : 2);
+          if (ph == 0) { pp[0] = t_act; pp[1] = t_full; pp[2] = t_peer; pp[7] = t_issue; pp[3] = PCLK() - t_begin; }
+          else { pp[0] = t_act; pp[1] = t_issue; }
         }
       }
     }
-  } else {
+  } else if (warp >= 2 && warp <= 9) {
     // ============ encode + epilogue warps ============
     const int q = warp & 3;                 // TMEM lane quarter
     const int hi = (warp - 2) >> 2;         // epilogue: column half ; encode: tile (0 = A, 1 = B)

@@ -209,13 +209,41 @@ __global__ void __launch_bounds__(288) tc_mma_rate1_kernel(int iters, int N, lon
     tc::mbar_wait(&bar, 0);
     out[blockIdx.x] = clock64() - t0;
     done = 1;
-  } else if (warp >= 1 && warp <= 4) {
+  } else if (warp >= 1 && warp <= ((mode & 128) ? 8 : 4)) {
     uint8_t* dst = smem + 80 * 1024;   // 64 KB scratch
     const int row = (warp - 1) * 32 + lane;
     uint32_t v[32];
     int c = 0;
     while (!done) {
-      if (mode & 2) { tc::tmem_ld32(tm + 256 + ((uint32_t)(((warp) & 3) * 32) << 16) + (c & 7) * 32, v); tc::tmem_wait_ld(); }
+      if (mode & 2) {
+        const int shape = (mode >> 4) & 3;
+        // 32x32b.x32 spans 32 columns, the 16-lane shapes span 64 columns for the same 4 KB
+        const uint32_t ta = tm + 256 + ((uint32_t)(((warp) & 3) * 32) << 16) + (shape == 0 ? (c & 7) * 32 : (c & 3) * 64);
+#define LD32(SHAPE)                                                                                              \
+  asm volatile("tcgen05.ld.sync.aligned." SHAPE ".b32 "                                                         \
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                         \
+               "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"         \
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),   \
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),          \
+                 "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),        \
+                 "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),        \
+                 "=r"(v[29]), "=r"(v[30]), "=r"(v[31])                                                            \
+               : "r"(ta)                                                                                          \
+               : "memory")
+        if (shape == 0) LD32("32x32b.x32");
+        else if (shape == 1) LD32("16x256b.x8");
+        else if (shape == 2) LD32("16x128b.x16");
+        else LD32("16x64b.x32");
+#undef LD32
+        if (mode & 64) {   // a second load in flight before the wait
+          uint32_t w[32];
+          tc::tmem_ld32(tm + 256 + ((uint32_t)(((warp) & 3) * 32) << 16) + ((c + 1) & 7) * 32, w);
+          tc::tmem_wait_ld();
+          v[0] += w[0];
+        } else {
+          tc::tmem_wait_ld();
+        }
+      }
       if (mode & 1) {
         uint4 q = make_uint4(v[0] + c, v[1], c, c);
         *reinterpret_cast<uint4*>(dst + (c & 31) * 2048 + (row >> 3) * 128 + (row & 7) * 16) = q;
@@ -225,7 +253,7 @@ __global__ void __launch_bounds__(288) tc_mma_rate1_kernel(int iters, int N, lon
     }
     if (c == 123456789) out[200] = v[3];
     if (warp == 1 && lane == 0) out[296 + blockIdx.x] = c;
-  } else if (warp == 5 && lane == 0 && (mode & 4)) {
+  } else if (warp == 5 && lane == 0 && (mode & 4) && !(mode & 128)) {
     uint8_t* dst = smem + 144 * 1024;  // 4 x 16 KB
     uint32_t g = 0;
     for (int i = 0; i < 4; ++i, ++g) { tc::mbar_arrive_expect_tx(&lbar[i], 16384); tc::bulk_g2s(dst + i * 16384, gsrc + (g % 64) * 16384, 16384, &lbar[i]); }
