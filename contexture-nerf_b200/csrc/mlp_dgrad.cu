@@ -95,8 +95,9 @@ mlp_dgrad_kernel(const __grid_constant__ DgradArgs a) {
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 10) {
     if (r != 0) {
+      if (warp == 1) {
       // ============ peer CTA: relay "my half landed" to the leader, once per chunk pair ============
       uint32_t g = 0;
       for (int64_t it = cid; it < n_citers; it += ncl)
@@ -111,46 +112,49 @@ mlp_dgrad_kernel(const __grid_constant__ DgradArgs a) {
             }
           }
         }
+      }
     } else {
-      // ============ leader CTA: MMA issuer for the pair ============
-      uint32_t g = 0, act_phase[2] = {0, 0};
+      // ============ leader CTA: two MMA issuers, warp 1 -> tile pair A, warp 10 -> tile pair B ============
+      // (one thread cannot issue fast enough to keep the tensor pipe fed; see mlp_fwd.cu)
+      const int ph = warp == 1 ? 0 : 1;
+      uint32_t gl = 0, act_phase = 0;
       const uint32_t idesc = tc::make_idesc_bf16(256, 256, 0, 0);
+      const uint32_t h_base = tc::smem_u32(h_buf + ph * kHBytes);
+      const uint32_t acc = tmem + ph * CTX_MLP_W;
       for (int64_t it = cid; it < n_citers; it += ncl) {
         for (int si = 0; si < n_steps; ++si) {
-          const int nchunks = net.L[a.step_src[si]].N / CTX_MLP_KC;
-#pragma unroll
-          for (int ph = 0; ph < 2; ++ph) {
-            tc::mbar_wait(&ctl->act_ready[ph], act_phase[ph]);
-            act_phase[ph] ^= 1;
-            tc::tc_fence_after();
-            const uint32_t h_base = tc::smem_u32(h_buf + ph * kHBytes);
-            for (int c = 0; c < nchunks; ++c, ++g) {
-              const int s = g % kDgStages, pr = s >> 1;
-              if (!(g & 1)) {
-                const uint32_t par = (g / kDgStages) & 1;
-                tc::mbar_wait(&ctl->full[pr], par);
-                tc::mbar_wait(&ctl->peer_full[pr], par);
-                tc::tc_fence_after();
-              }
-              const uint32_t a_base = h_base + c * 4 * kK8Stride;
-              const uint32_t b_base = tc::smem_u32(w_buf + s * kDgStageBytes);
-              if (tc::elect_one()) {
-#pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                  const uint64_t da = tc::make_smem_desc(a_base + kk * 2 * kK8Stride, kK8Stride, 128);
-                  const uint64_t db = tc::make_smem_desc(b_base + kk * 2 * 2048, 2048, 128);
-                  tc::mma2_bf16_ss(tmem + ph * CTX_MLP_W, da, db, idesc, (c > 0 || kk > 0) ? 1u : 0u);
-                }
-                if (c == nchunks - 1) tc::mma2_commit(&ctl->acc_full[ph]);
-                if (g & 1) tc::mma2_commit(&ctl->empty[pr]);
-              }
-              __syncwarp();
+          const int nchunks = net.L[a.step_src[si]].N / CTX_MLP_KC;   // 4 or 8: phases are whole chunk pairs
+          uint32_t g = gl + ph * nchunks;
+          gl += 2 * nchunks;
+          tc::mbar_wait(&ctl->act_ready[ph], act_phase);
+          act_phase ^= 1;
+          tc::tc_fence_after();
+          for (int c = 0; c < nchunks; ++c, ++g) {
+            const int s = g % kDgStages, pr = s >> 1;
+            if (!(g & 1)) {
+              const uint32_t par = (g / kDgStages) & 1;
+              tc::mbar_wait(&ctl->full[pr], par);
+              tc::mbar_wait(&ctl->peer_full[pr], par);
+              tc::tc_fence_after();
             }
+            const uint32_t a_base = h_base + c * 4 * kK8Stride;
+            const uint32_t b_base = tc::smem_u32(w_buf + s * kDgStageBytes);
+            if (tc::elect_one()) {
+#pragma unroll
+              for (int kk = 0; kk < 2; ++kk) {
+                const uint64_t da = tc::make_smem_desc(a_base + kk * 2 * kK8Stride, kK8Stride, 128);
+                const uint64_t db = tc::make_smem_desc(b_base + kk * 2 * 2048, 2048, 128);
+                tc::mma2_bf16_ss(acc, da, db, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+              }
+              if (c == nchunks - 1) tc::mma2_commit(&ctl->acc_full[ph]);
+              if (g & 1) tc::mma2_commit(&ctl->empty[pr]);
+            }
+            __syncwarp();
           }
         }
       }
     }
-  } else {
+  } else if (warp >= 2 && warp <= 9) {
     // ============ head-init + epilogue warps ============
     const int q = warp & 3;                 // TMEM lane quarter
     const int hi = (warp - 2) >> 2;         // epilogue: column half ; head init: tile (0 = A, 1 = B)
