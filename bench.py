@@ -226,17 +226,32 @@ def main():
     kern = {}
     for name, evs in (timers or {}).items():
         kern[name] = sum(x.elapsed_time(y) for x, y in evs) / len(evs)
-    flops = {"mlp_fwd_coarse": 2.0 * MACS_PER_EVAL * RAYS_PER_GPU * N_SAMPLES,
-             "mlp_fwd_fine": 2.0 * MACS_PER_EVAL * RAYS_PER_GPU * (N_SAMPLES + N_IMPORTANCE)}
-    flops["mlp_bwd_coarse"] = 2 * flops["mlp_fwd_coarse"]
-    flops["mlp_bwd_fine"] = 2 * flops["mlp_fwd_fine"]
+    pts = {"coarse": RAYS_PER_GPU * N_SAMPLES, "fine": RAYS_PER_GPU * (N_SAMPLES + N_IMPORTANCE)}
+    WGRAD_BYTES_PER_POINT = 11392.0      # sum over the 14 wgrad jobs of (A + B channels) x 2 B, DESIGN.md section 4
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            traffic = json.load(fh)
+    except Exception:
+        pass
+    kernels = {}
+    for name, t_ms in kern.items():
+        _, kind, net = name.split("_")
+        n = pts[net]
+        if kind == "wgrad":       # HBM-bound: operands are streamed once from the records
+            ach = WGRAD_BYTES_PER_POINT * n / (t_ms * 1e-3) / 1e9
+            kernels[name] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                             "frac": ach / pk["hbm_gbs"], "ms_per_launch": t_ms}
+        else:                     # fwd / dgrad: one pass of 593 408 MAC per point
+            ach = 2.0 * MACS_PER_EVAL * n / (t_ms * 1e-3) / 1e12
+            kernels[name] = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                             "frac": ach / pk["tf_sustained"], "ms_per_launch": t_ms}
     dom = max(kern, key=kern.get) if kern else None
     roofline = None
     if dom:
-        ach = flops[dom] / (kern[dom] * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": pk["source"] + " (sustained)",
-                    "ms_per_launch": kern[dom]}
+        roofline = dict(kernels[dom], kernel=dom, traffic=traffic.get(dom),
+                        peak_source=pk["source"] + (" copy bandwidth" if kernels[dom]["bound"] == "hbm"
+                                                    else " cuBLAS bf16, sustained"))
     step_flops = 3 * 2.0 * MACS_PER_EVAL * RAYS_PER_GPU * EVALS_PER_RAY
     line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -245,7 +260,7 @@ def main():
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "roofline": roofline,
             "step_tensor_frac": step_flops / (ms / args.steps * 1e-3) / 1e12 / pk["tf_sustained"],
-            "kernel_ms": kern, "final_loss": final_loss}
+            "kernels": kernels, "final_loss": final_loss}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

@@ -232,10 +232,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const __grid_c
 
 // grads: HOST array of DEVICE pointers in the order of ctx_mlp_pack's `params`
 // (gradients are ACCUMULATED into them: zero them first for a fresh gradient).
-extern "C" int ctx_mlp_bwd(const void* net_host, const void* wtpacked, const float* fparams,
-                           const float* g_out, const void* acts, void* dacts, int64_t P, float* const* grads,
-                           int n_grads, void* stream) {
-  if (!net_host || !wtpacked || !fparams || !g_out || !acts || !dacts || !grads || P < 0) return CTX_ERR_BAD_ARG;
+extern "C" int ctx_mlp_wgrad(const void* net_host, const void* acts, const void* dacts, int64_t P,
+                             float* const* grads, int n_grads, void* stream) {
+  if (!net_host || !acts || !dacts || !grads || P < 0) return CTX_ERR_BAD_ARG;
   if (P == 0) return 0;
   const CtxMlpNet& net = *reinterpret_cast<const CtxMlpNet*>(net_host);
   const bool views = net.in_views > 0;
@@ -245,14 +244,9 @@ extern "C" int ctx_mlp_bwd(const void* net_host, const void* wtpacked, const flo
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(ctx::mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)ctx::kWgSmemBytes);
+                                         (int)ctx::kWgSmemBytes);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
-  }
-  // ---------------- dgrad ----------------
-  {
-    const int rc = ctx_launch_dgrad(net, wtpacked, fparams, g_out, acts, dacts, P, st);
-    if (rc != 0) return rc;
   }
   // ---------------- wgrad ----------------
   {
@@ -331,4 +325,20 @@ extern "C" int ctx_mlp_bwd(const void* net_host, const void* wtpacked, const flo
     ctx::mlp_wgrad_kernel<<<begin, ctx::kWgThreads, ctx::kWgSmemBytes, st>>>(w);
   }
   CTX_RETURN_LAST();
+}
+
+extern "C" int ctx_mlp_dgrad(const void* net_host, const void* wtpacked, const float* fparams, const float* g_out,
+                             const void* acts, void* dacts, int64_t P, void* stream) {
+  if (!net_host || !wtpacked || !fparams || !g_out || !acts || !dacts || P < 0) return CTX_ERR_BAD_ARG;
+  if (P == 0) return 0;
+  return ctx_launch_dgrad(*reinterpret_cast<const CtxMlpNet*>(net_host), wtpacked, fparams, g_out, acts, dacts, P,
+                          (cudaStream_t)stream);
+}
+
+extern "C" int ctx_mlp_bwd(const void* net_host, const void* wtpacked, const float* fparams,
+                           const float* g_out, const void* acts, void* dacts, int64_t P, float* const* grads,
+                           int n_grads, void* stream) {
+  const int rc = ctx_mlp_dgrad(net_host, wtpacked, fparams, g_out, acts, dacts, P, stream);
+  if (rc != 0) return rc;
+  return ctx_mlp_wgrad(net_host, acts, dacts, P, grads, n_grads, stream);
 }

@@ -18,31 +18,39 @@ __device__ __forceinline__ float enc_freq(int k, int L, int log_sampling) {
   return linspace_at(1.0f, exp2f((float)(L - 1)), L, k);         // linear in frequency
 }
 
+// One thread per (point, coordinate): it loops over the L frequencies, so no index division sits on the hot
+// path and x is read once.  The tile is assembled in shared memory and leaves with 16-byte coalesced stores.
+template <int D>
 __global__ void __launch_bounds__(kEncThreads)
-posenc_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n, int d, int L,
+posenc_fwd_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n, int d_rt, int L,
                   int inc, int log_sampling) {
   extern __shared__ __align__(16) float tile[];
+  const int d = D > 0 ? D : d_rt;
   const int C = d * (inc + 2 * L);
   const int64_t ntiles = ceil_div(n, kEncTile);
   for (int64_t tix = blockIdx.x; tix < ntiles; tix += gridDim.x) {
     const int64_t p0 = tix * kEncTile;
     const int np = (int)min((int64_t)kEncTile, n - p0);
-    if (inc) {
-      for (int e = threadIdx.x; e < np * d; e += kEncThreads) {
-        const int pt = e / d, j = e - pt * d;
-        tile[pt * C + j] = x[(p0 + pt) * d + j];
+    for (int e = threadIdx.x; e < np * d; e += kEncThreads) {
+      const int pt = e / d, j = e - pt * d;
+      const float xv = x[p0 * d + e];
+      float* row = tile + pt * C;
+      if (inc) row[j] = xv;
+      float* o = row + inc * d + j;
+      if (log_sampling) {
+        float f = 1.0f;
+        for (int k = 0; k < L; ++k, f *= 2.0f, o += 2 * d) {
+          float s, c;
+          sincosf(__fmul_rn(xv, f), &s, &c);
+          o[0] = s; o[d] = c;
+        }
+      } else {
+        for (int k = 0; k < L; ++k, o += 2 * d) {
+          float s, c;
+          sincosf(__fmul_rn(xv, enc_freq(k, L, 0)), &s, &c);
+          o[0] = s; o[d] = c;
+        }
       }
-    }
-    const int per_pt = d * L;
-    for (int e = threadIdx.x; e < np * per_pt; e += kEncThreads) {
-      const int pt = e / per_pt, rem = e - pt * per_pt;
-      const int k = rem / d, j = rem - k * d;
-      const float arg = __fmul_rn(x[(p0 + pt) * d + j], enc_freq(k, L, log_sampling));
-      float s, c;
-      sincosf(arg, &s, &c);
-      float* row = tile + pt * C + inc * d + k * 2 * d;
-      row[j] = s;
-      row[d + j] = c;
     }
     __syncthreads();
     float* dst = out + p0 * C;
@@ -99,15 +107,21 @@ extern "C" int ctx_posenc_fwd(const float* x, float* out, int64_t n, int d, int 
   const int C = d * ((include_input ? 1 : 0) + 2 * L);
   const size_t smem = (size_t)ctx::kEncTile * C * sizeof(float);
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(ctx::posenc_fwd_kernel,
+    cudaError_t e = cudaFuncSetAttribute(ctx::posenc_fwd_kernel<0>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
   int64_t blocks = ctx::ceil_div(n, ctx::kEncTile);
   const int64_t cap = (int64_t)ctx::kNumSMs * 12;
   if (blocks > cap) blocks = cap;
-  ctx::posenc_fwd_kernel<<<(int)blocks, ctx::kEncThreads, smem, (cudaStream_t)stream>>>(
-      x, out, n, d, L, include_input ? 1 : 0, log_sampling);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int inc = include_input ? 1 : 0;
+  if (d == 3 && smem <= 48 * 1024)
+    ctx::posenc_fwd_kernel<3><<<(int)blocks, ctx::kEncThreads, smem, st>>>(x, out, n, d, L, inc, log_sampling);
+  else if (d == 2 && smem <= 48 * 1024)
+    ctx::posenc_fwd_kernel<2><<<(int)blocks, ctx::kEncThreads, smem, st>>>(x, out, n, d, L, inc, log_sampling);
+  else
+    ctx::posenc_fwd_kernel<0><<<(int)blocks, ctx::kEncThreads, smem, st>>>(x, out, n, d, L, inc, log_sampling);
   CTX_RETURN_LAST();
 }
 

@@ -57,6 +57,65 @@ __device__ __forceinline__ float stratified_depth(float near, float far, int S, 
   return lower + (upper - lower) * u;
 }
 
+// One warp writes the S depths of a ray: each lane produces QUADS of consecutive samples (one Philox call =
+// 4 uniforms, one 16-byte store), the linspace step and the reciprocals are hoisted.  Values are bit-identical
+// to stratified_depth() sample by sample.
+// `lane` / `nl`: position in and size of the lane group that shares this ray (8, 16 or 32 lanes).
+__device__ __forceinline__ void write_z_row(float* __restrict__ zrow, float near, float far, int S, int lindisp,
+                                            int perturb, const float* __restrict__ jrow, uint64_t seed,
+                                            uint64_t ray, int lane, int nl = 32) {
+  if ((S & 3) != 0 || S < 4) {   // ragged sample counts: element-wise path
+    for (int s = lane; s < S; s += nl) {
+      float u = 0.f;
+      if (perturb) u = jrow ? jrow[s] : philox_uniform(seed, 0, ray, (uint32_t)s);
+      zrow[s] = stratified_depth(near, far, S, s, lindisp, perturb != 0, u);
+    }
+    return;
+  }
+  const float step = __fdiv_rn(1.0f, (float)(S - 1));
+  const float inear = 1.0f / near, ifar = 1.0f / far;
+  const int half = S / 2;
+  auto base = [&](int i) -> float {
+    const float t = (i < half) ? fmaf(step, (float)i, 0.0f) : fmaf(-step, (float)(S - 1 - i), 1.0f);
+    if (lindisp) return 1.0f / (inear * (1.0f - t) + ifar * t);
+    return near * (1.0f - t) + far * t;
+  };
+  for (int q = lane; q < (S >> 2); q += nl) {
+    const int s0 = q << 2;
+    float4 out;
+    if (!perturb) {
+      out = make_float4(base(s0), base(s0 + 1), base(s0 + 2), base(s0 + 3));
+    } else {
+      float zb[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int si = min(max(s0 - 1 + i, 0), S - 1);
+        zb[i] = base(si);
+      }
+      float u[4];
+      if (jrow) {
+        const float4 j4 = *reinterpret_cast<const float4*>(jrow + s0);
+        u[0] = j4.x; u[1] = j4.y; u[2] = j4.z; u[3] = j4.w;
+      } else {
+        Philox ph(seed);
+        const uint4 rr = ph(ray, (uint64_t)q);   // stream 0: same numbers as philox_uniform(seed, 0, ray, s)
+        u[0] = u01(rr.x); u[1] = u01(rr.y); u[2] = u01(rr.z); u[3] = u01(rr.w);
+      }
+      float o[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int s = s0 + i;
+        const float zc = zb[i + 1];
+        const float lower = (s == 0) ? zc : 0.5f * (zc + zb[i]);
+        const float upper = (s == S - 1) ? zc : 0.5f * (zb[i + 2] + zc);
+        o[i] = lower + (upper - lower) * u[i];
+      }
+      out = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    *reinterpret_cast<float4*>(zrow + s0) = out;
+  }
+}
+
 __device__ __forceinline__ void ndc_warp(int H, int W, float focal, float near, float& ox,
                                          float& oy, float& oz, float& dx, float& dy, float& dz) {
   const float t = -(near + oz) / dz;
@@ -72,9 +131,12 @@ __device__ __forceinline__ void ndc_warp(int H, int W, float focal, float near, 
 }
 
 __global__ void __launch_bounds__(kRayWarps * 32) raygen_kernel(RaygenParams p) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp0 = (int64_t)blockIdx.x * kRayWarps + (threadIdx.x >> 5);
-  const int64_t nwarps = (int64_t)gridDim.x * kRayWarps;
+  // a group of `nl` lanes (8/16/32, chosen so that one pass of quads covers the S depths) shares a ray
+  const int nl = p.n_samples > 64 ? 32 : (p.n_samples > 32 ? 16 : 8);
+  const int gpw = 32 / nl;                                   // rays per warp per iteration
+  const int lane = (threadIdx.x & 31) & (nl - 1);
+  const int64_t warp0 = ((int64_t)blockIdx.x * kRayWarps + (threadIdx.x >> 5)) * gpw + ((threadIdx.x & 31) / nl);
+  const int64_t nwarps = (int64_t)gridDim.x * kRayWarps * gpw;
   // camera (uniform loads)
   float rot[3][3], org[3];
 #pragma unroll
@@ -119,14 +181,9 @@ __global__ void __launch_bounds__(kRayWarps * 32) raygen_kernel(RaygenParams p) 
       if (p.viewdirs) p.viewdirs[r * 3 + lane] = lane == 0 ? vx : lane == 1 ? vy : vz;
     }
     if (p.near_far && lane < 2) p.near_far[r * 2 + lane] = lane == 0 ? near : far;
-    if (p.z_vals) {
-      const int S = p.n_samples;
-      for (int s = lane; s < S; s += 32) {
-        float u = 0.f;
-        if (p.perturb) u = p.jitter ? p.jitter[r * S + s] : philox_uniform(p.seed, 0, (uint64_t)r, (uint32_t)s);
-        p.z_vals[r * S + s] = stratified_depth(near, far, S, s, p.lindisp, p.perturb != 0, u);
-      }
-    }
+    if (p.z_vals)
+      write_z_row(p.z_vals + r * p.n_samples, near, far, p.n_samples, p.lindisp, p.perturb,
+                  p.jitter ? p.jitter + r * p.n_samples : nullptr, p.seed, (uint64_t)r, lane, nl);
   }
 }
 
@@ -140,11 +197,7 @@ stratified_kernel(const float* __restrict__ near, int64_t near_stride, const flo
   const int64_t nwarps = (int64_t)gridDim.x * kRayWarps;
   for (int64_t r = warp0; r < R; r += nwarps) {
     const float n = near[r * near_stride], f = far[r * far_stride];
-    for (int s = lane; s < S; s += 32) {
-      float u = 0.f;
-      if (perturb) u = jitter ? jitter[r * S + s] : philox_uniform(seed, 0, (uint64_t)r, (uint32_t)s);
-      z_vals[r * S + s] = stratified_depth(n, f, S, s, lindisp, perturb != 0, u);
-    }
+    write_z_row(z_vals + r * S, n, f, S, lindisp, perturb, jitter ? jitter + r * S : nullptr, seed, (uint64_t)r, lane);
   }
 }
 

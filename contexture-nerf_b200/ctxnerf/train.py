@@ -120,11 +120,12 @@ class NerfTrainer:
             call("ctx_mse_fwd_bwd", ptr(f["comp_f"][0]), ptr(f["comp_c"][0]), ptr(target), R * 3, 1.0,
                  ptr(self._loss), ptr(g_rgb), ptr(g_rgb0), stream_ptr(dev))
             g_raw_f = self._composite_bwd(f["raw_f"], f["z_f"], f["d"], R, Sf, g_rgb)
-            self._timed("mlp_bwd_fine", lambda: mlp_backward(self.fine, f["pk_f"], f["acts_f"], f["Pf"], g_raw_f,
-                                                             sinks=self.bucket.sinks_for(self.fine)))
+            mlp_backward(self.fine, f["pk_f"], f["acts_f"], f["Pf"], g_raw_f, sinks=self.bucket.sinks_for(self.fine),
+                         timed=lambda n, fn: self._timed(f"mlp_{n}_fine", fn))
             g_raw_c = self._composite_bwd(f["raw_c"], f["z_c"], f["d"], R, S, g_rgb0)
-            self._timed("mlp_bwd_coarse", lambda: mlp_backward(self.coarse, f["pk_c"], f["acts_c"], f["Pc"], g_raw_c,
-                                                               sinks=self.bucket.sinks_for(self.coarse)))
+            mlp_backward(self.coarse, f["pk_c"], f["acts_c"], f["Pc"], g_raw_c,
+                         sinks=self.bucket.sinks_for(self.coarse),
+                         timed=lambda n, fn: self._timed(f"mlp_{n}_coarse", fn))
             self.bucket.all_reduce()
             if optimizer_step:
                 self.step_count += 1

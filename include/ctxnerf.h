@@ -133,6 +133,12 @@ int ctx_mlp_fwd(const void* net, const void* wpacked, const float* fparams, int 
 int ctx_mlp_bwd(const void* net, const void* wtpacked, const float* fparams, const float* g_out,
                 const void* acts, void* dacts, int64_t P, float* const* grads, int n_grads,
                 void* stream);
+/* the two halves of ctx_mlp_bwd, separately launchable (and separately timed by bench.py):
+ * dgrad fills the dZ records from g_out, wgrad reduces records + dZ records into the gradients. */
+int ctx_mlp_dgrad(const void* net, const void* wtpacked, const float* fparams, const float* g_out,
+                  const void* acts, void* dacts, int64_t P, void* stream);
+int ctx_mlp_wgrad(const void* net, const void* acts, const void* dacts, int64_t P, float* const* grads,
+                  int n_grads, void* stream);
 
 /* ---- training-step glue ------------------------------------------------------
  * img2mse(a,t) + img2mse(b,t) (src/run_nerf_helpers.py:9) and its gradient in one
