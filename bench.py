@@ -58,7 +58,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except Exception:
@@ -66,15 +66,27 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def wait_first_sample(self, timeout=5.0):
+        """nvidia-smi needs a moment to start; block until it has produced a line."""
+        t0 = time.time()
+        while self.proc is not None and not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark(self):
+        self.t_mark = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        t_lo = getattr(self, "t_mark", 0.0) - 0.06      # samples taken during the timed region
+        for ts, ln in self.lines:
+            if ts < t_lo:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -187,16 +199,18 @@ def main():
             dist.barrier()
 
     def timed(step_fn, steps, with_timers):
+        cs = ClockSampler(local)
+        cs.start()
         for i in range(warm):
             step_fn(i)
         torch.cuda.synchronize()
+        cs.wait_first_sample()
         barrier()
         tr.timers = {} if with_timers else None
         l0 = _lib.launch_count
-        cs = ClockSampler(local)
-        cs.start()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
+        cs.mark()
         a.record()
         for i in range(steps):
             step_fn(warm + i)

@@ -107,6 +107,20 @@ class NerfTrainer:
         return dict(rgb_map=rgb, disp_map=disp, acc_map=acc, depth_map=depth, rgb0=fwd["comp_c"][0])
 
     @torch.no_grad()
+    def render_view(self, H, W, K, c2w, n_samples=192, sphere=None, near=None, far=None):
+        """Single-pass render of a whole view with the fine network (BASELINE config 4: per-ray near/far from
+        the bounding sphere of the normalised mesh, `n_samples` depths per ray, no hierarchical pass)."""
+        dev = self.device
+        with torch.cuda.device(dev):
+            r = ops.raygen(H, W, K, torch.as_tensor(c2w, dtype=torch.float32).to(dev), n_samples=n_samples,
+                           near=self.near if near is None else near, far=self.far if far is None else far,
+                           sphere=sphere, want_viewdirs=True)
+            raw, _, _, _ = forward_raw(self.fine, rays=(r["rays_o"], r["rays_d"], r["viewdirs"], r["z_vals"]))
+            rgb, disp, acc, _, depth = self._composite(raw, r["z_vals"], r["rays_d"], H * W, n_samples)
+        return dict(rgb_map=rgb.reshape(H, W, 3), disp_map=disp.reshape(H, W), acc_map=acc.reshape(H, W),
+                    depth_map=depth.reshape(H, W))
+
+    @torch.no_grad()
     def step(self, ray_idx: torch.Tensor, target: torch.Tensor, optimizer_step: bool = True) -> torch.Tensor:
         """One training step on this rank's ray batch; returns the loss (device scalar)."""
         dev = self.device
