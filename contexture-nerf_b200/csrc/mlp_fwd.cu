@@ -40,7 +40,7 @@ struct __align__(8) Mlp2SmemCtl {
 constexpr size_t kMlp2SmemBytes = (size_t)kTiles * (kHBytes + kXBytes) + (size_t)kStages2 * kStage2Bytes +
                                   kHeadFloats * 4 + 256;
 
-template <int PAD, int MAXL>
+template <int PAD, int MAXL, int D = 3>
 __device__ __forceinline__ void encode_row2(uint8_t* tile, int row, const float* xyz, int L, bool valid,
                                             uint8_t* gtile) {
   float v[PAD];
@@ -48,17 +48,17 @@ __device__ __forceinline__ void encode_row2(uint8_t* tile, int row, const float*
   for (int i = 0; i < PAD; ++i) v[i] = 0.f;
   if (valid) {
 #pragma unroll
-    for (int j = 0; j < 3; ++j) v[j] = xyz[j];
+    for (int j = 0; j < D; ++j) v[j] = xyz[j];
 #pragma unroll
     for (int k = 0; k < MAXL; ++k) {
       if (k < L) {
         const float f = (float)(1 << k);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
+        for (int j = 0; j < D; ++j) {
           float s, c;
           fast_sincos(xyz[j] * f, s, c);
-          const int b = 3 + k * 6;
-          if (b + 3 + j < PAD) { v[b + j] = s; v[b + 3 + j] = c; }
+          const int b = D + k * 2 * D;
+          if (b + D + j < PAD) { v[b + j] = s; v[b + D + j] = c; }
         }
       }
     }
@@ -267,6 +267,17 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
           for (int j = 0; j < 3; ++j) xyz[j] = a.rays_o[ry * 3 + j] + a.rays_d[ry * 3 + j] * zv;
         }
         encode_row2<CTX_MLP_XP_PAD, 10>(my_x, row, xyz, a.L_pts, valid, rec ? rec + net.xp_slot : nullptr);
+      } else if (a.mode == 2) {
+        // UV grid of the texture atlas (reference get_texture_map, src/models/textured_mesh.py:266-272):
+        // point p = y*res + x  ->  (u, v) = (linspace(0,1,res)[x], linspace(0,1,res)[y]), encoded in place
+        float uv[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+          const int res = a.S;
+          const int py = (int)(p / res), px = (int)(p - (int64_t)py * res);
+          uv[0] = linspace_at(0.0f, 1.0f, res, px);
+          uv[1] = linspace_at(0.0f, 1.0f, res, py);
+        }
+        encode_row2<CTX_MLP_XP_PAD, 10, 2>(my_x, row, uv, a.L_pts, valid, rec ? rec + net.xp_slot : nullptr);
       } else {
         float v[CTX_MLP_XP_PAD];
 #pragma unroll
@@ -449,6 +460,9 @@ extern "C" int ctx_mlp_fwd(const void* net_host, const void* wpacked, const floa
     if (!rays_o || !rays_d || !z || S < 1 || (a.net.in_views > 0 && !viewdirs)) return CTX_ERR_BAD_ARG;
     if (a.net.in_pts != 3 * (1 + 2 * L_pts) || L_pts > 10) return CTX_ERR_UNSUPPORTED;
     if (a.net.in_views > 0 && (a.net.in_views != 3 * (1 + 2 * L_dirs) || L_dirs > 4)) return CTX_ERR_UNSUPPORTED;
+  } else if (mode == 2) {
+    if (S < 2 || (int64_t)S * S != P || a.net.in_views != 0) return CTX_ERR_BAD_ARG;
+    if (a.net.in_pts != 2 * (1 + 2 * L_pts) || L_pts > 10) return CTX_ERR_UNSUPPORTED;
   } else {
     return CTX_ERR_BAD_ARG;
   }

@@ -49,7 +49,44 @@ __global__ void mse_pair_kernel(const float* __restrict__ a, const float* __rest
   }
 }
 
+// texture activation of the reference: (tanh(x)+1)/2 (src/models/textured_mesh.py:299), fused with the
+// [P,C] -> [C,P] (NCHW) transpose of `.reshape(1,res,res,3).permute(0,3,1,2)`.
+__global__ void tanh01_fwd_kernel(const float* __restrict__ raw, float* __restrict__ out, int64_t P, int C) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x)
+    for (int c = 0; c < C; ++c) out[(int64_t)c * P + i] = (tanhf(raw[i * C + c]) + 1.0f) * 0.5f;
+}
+// g_raw[p,c] = g_raw_in[p,c] (optional) + g_tex[c,p] * 0.5 * (1 - tanh(raw)^2)
+__global__ void tanh01_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ g_tex,
+                                  const float* __restrict__ g_raw_in, float* __restrict__ g_raw, int64_t P, int C) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x)
+    for (int c = 0; c < C; ++c) {
+      const float t = tanhf(raw[i * C + c]);
+      float g = g_tex ? g_tex[(int64_t)c * P + i] * 0.5f * (1.0f - t * t) : 0.f;
+      if (g_raw_in) g += g_raw_in[i * C + c];
+      g_raw[i * C + c] = g;
+    }
+}
+
 }  // namespace ctx
+
+extern "C" int ctx_tanh01_fwd(const float* raw, float* out, int64_t P, int C, void* stream) {
+  if (P < 0 || C < 1 || !raw || !out) return CTX_ERR_BAD_ARG;
+  if (P == 0) return 0;
+  int64_t blocks = ctx::ceil_div(P, 256);
+  if (blocks > ctx::kNumSMs * 8) blocks = ctx::kNumSMs * 8;
+  ctx::tanh01_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(raw, out, P, C);
+  CTX_RETURN_LAST();
+}
+
+extern "C" int ctx_tanh01_bwd(const float* raw, const float* g_tex, const float* g_raw_in, float* g_raw, int64_t P,
+                              int C, void* stream) {
+  if (P < 0 || C < 1 || !raw || !g_raw) return CTX_ERR_BAD_ARG;
+  if (P == 0) return 0;
+  int64_t blocks = ctx::ceil_div(P, 256);
+  if (blocks > ctx::kNumSMs * 8) blocks = ctx::kNumSMs * 8;
+  ctx::tanh01_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(raw, g_tex, g_raw_in, g_raw, P, C);
+  CTX_RETURN_LAST();
+}
 
 extern "C" int ctx_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                              float lr, float beta1, float beta2, float eps, int step, float weight_decay,

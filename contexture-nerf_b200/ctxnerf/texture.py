@@ -1,0 +1,62 @@
+"""Fused ``get_texture_map`` of the reference's TexturedMeshModel
+(/root/reference/src/models/textured_mesh.py:266-301): UV grid -> 2-D L=10 positional encoding -> NeRF2D
+42->3 -> (tanh+1)/2 -> [1,3,res,res], forward and backward, without materialising the grid or its encoding.
+
+Drop-in use inside the reference::
+
+    from ctxnerf.texture import get_texture_map
+    TexturedMeshModel.get_texture_map = lambda self: get_texture_map(self.texture_mlp, self.texture_resolution)
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import call, ptr, stream_ptr
+from .mlp import TILE
+from .mlp_bwd import mlp_backward
+
+
+class _TextureMapFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, res, need_grad, *params):
+        module._ensure()
+        desc = module._desc
+        if desc.in_views != 0 or desc.in_pts != 2 * (1 + 2 * module.L_pts):
+            raise _lib.CtxNerfError("get_texture_map needs the 2-D texture MLP (input_ch = 2*(1+2*multires), no views)")
+        dev = params[0].device
+        P = res * res
+        packed = module._packed.get(list(params))
+        w, wt, f = packed
+        raw = torch.empty(P, desc.out_ch, device=dev, dtype=torch.float32)
+        acts = None
+        if need_grad:
+            ntiles = 4 * ((P + 4 * TILE - 1) // (4 * TILE))
+            acts = torch.empty(ntiles * desc.act_tile_bytes, dtype=torch.uint8, device=dev)
+        tex = torch.empty(1, desc.out_ch, res, res, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            call("ctx_mlp_fwd", desc.p, ptr(w), ptr(f), 2, None, 0, None, None, None, None, res, module.L_pts, 0, P,
+                 ptr(raw), ptr(acts), stream_ptr(dev))
+            call("ctx_tanh01_fwd", ptr(raw), ptr(tex), P, desc.out_ch, stream_ptr(dev))
+        ctx.module, ctx.P, ctx.acts, ctx.packed, ctx.raw = module, P, acts, packed, raw
+        return tex, raw
+
+    @staticmethod
+    def backward(ctx, g_tex, g_raw_in):
+        desc = ctx.module._desc
+        dev = ctx.raw.device
+        g_raw = torch.empty_like(ctx.raw)
+        gt = g_tex.float().contiguous() if g_tex is not None else None
+        gi = g_raw_in.float().contiguous() if g_raw_in is not None else None
+        with torch.cuda.device(dev):
+            call("ctx_tanh01_bwd", ptr(ctx.raw), ptr(gt), ptr(gi), ptr(g_raw), ctx.P, desc.out_ch, stream_ptr(dev))
+        grads = mlp_backward(ctx.module, ctx.packed, ctx.acts, ctx.P, g_raw)
+        ctx.acts = None
+        return (None, None, None) + tuple(grads)
+
+
+def get_texture_map(texture_mlp, res: int):
+    """-> (texture [1,3,res,res] in [0,1], mlp_output [res*res,3]) like the reference method."""
+    params = texture_mlp._param_list()
+    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    return _TextureMapFn.apply(texture_mlp, int(res), need_grad, *params)

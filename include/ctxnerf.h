@@ -114,7 +114,8 @@ int ctx_mlp_describe(int D, uint32_t skip_mask, int in_pts, int in_views, int ou
  * buffers sized from the net blob (see contexture-nerf_b200/csrc/mlp_desc.h).   */
 int ctx_mlp_pack(const void* net, const float* const* params, int n_params, void* wpacked,
                  void* wtpacked, float* fparams, void* stream);
-/* mode 0: x [P,x_ld] holds the already-encoded input [pts_enc | view_enc];
+/* mode 2: UV-grid texture query, see ctx_tanh01_fwd below.
+ * mode 0: x [P,x_ld] holds the already-encoded input [pts_enc | view_enc];
  * mode 1: the P = R*S points o + d*z (z [R,S]) and the view directions are
  * encoded in-kernel straight into shared memory (Embedder.embed :44-45, L_pts
  * / L_dirs frequencies).  out [P,out_ch] raw network output (no activation,
@@ -139,6 +140,16 @@ int ctx_mlp_dgrad(const void* net, const void* wtpacked, const float* fparams, c
                   const void* acts, void* dacts, int64_t P, void* stream);
 int ctx_mlp_wgrad(const void* net, const void* acts, const void* dacts, int64_t P, float* const* grads,
                   int n_grads, void* stream);
+
+/* ---- fused texture map: get_texture_map, src/models/textured_mesh.py:266-301 -----------------------
+ * ctx_mlp_fwd mode 2 generates the res x res UV grid (meshgrid of linspace(0,1,res), 'xy' indexing, :269-272),
+ * encodes it (L_pts frequencies, 2-D) in shared memory and runs the 42->3 texture MLP: pass x = NULL, S = res,
+ * P = res*res.  ctx_tanh01_fwd then applies (tanh+1)/2 (:299) and writes the NCHW layout [C, P] of
+ * `.reshape(1,res,res,3).permute(0,3,1,2)`; ctx_tanh01_bwd is its backward (g_raw_in nullable: extra gradient
+ * arriving directly on mlp_output).                                                                      */
+int ctx_tanh01_fwd(const float* raw, float* out, int64_t P, int C, void* stream);
+int ctx_tanh01_bwd(const float* raw, const float* g_tex, const float* g_raw_in, float* g_raw, int64_t P, int C,
+                   void* stream);
 
 /* ---- training-step glue ------------------------------------------------------
  * img2mse(a,t) + img2mse(b,t) (src/run_nerf_helpers.py:9) and its gradient in one

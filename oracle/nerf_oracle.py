@@ -380,6 +380,23 @@ def render_rays(ray_batch: torch.Tensor, network_fn, network_query_fn: Callable,
     return out
 
 
+def texture_uv_grid(res: int) -> torch.Tensor:
+    """UV grid of get_texture_map (/root/reference/src/models/textured_mesh.py:268-272): meshgrid of two
+    linspace(0,1,res) with 'xy' indexing, stacked (u,v) and flattened row-major -> [res*res, 2]."""
+    lin = torch.linspace(0, 1, res, dtype=torch.float32)
+    u, v = torch.meshgrid(lin, lin, indexing="xy")
+    return torch.stack([u, v], -1).reshape(-1, 2)
+
+
+def texture_map(params, res: int, multires: int = 10, bf16_operands: bool = False):
+    """get_texture_map (textured_mesh.py:266-301): -> (texture [1,3,res,res], mlp_output [res*res,3])."""
+    enc = posenc(texture_uv_grid(res), multires)
+    fwd = mlp_forward_bf16 if bf16_operands else mlp_forward
+    out = fwd(params, enc)
+    tex = (torch.tanh(out) + 1) / 2
+    return tex.reshape(1, res, res, 3).permute(0, 3, 1, 2), out
+
+
 def img2mse(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     """reference :9"""
     return torch.mean((x - y) ** 2)

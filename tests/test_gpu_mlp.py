@@ -193,3 +193,37 @@ def test_mlp_backward_fused_rays_training_step(cuda):
     # the optimiser consumes; require cosine >= 0.999 and <= 4 % L2 deviation of the full gradient vector
     for tag, (l2, cos) in worst_all.items():
         assert cos > 0.999 and l2 < 0.04, (tag, l2, cos)
+
+
+@pytest.mark.parametrize("res", [64, 200])
+def test_fused_texture_map_forward_and_backward(cuda, res):
+    """get_texture_map (textured_mesh.py:266-301) as one fused query: UV grid + 2-D encoding generated inside the
+    MLP kernel, (tanh+1)/2 + NCHW transpose after it; backward vs autograd through the oracle."""
+    from ctxnerf.texture import get_texture_map
+    net, params = _net(cuda, False, seed=res, in_pts=42, out_ch=3)
+    tex, raw = get_texture_map(net, res)
+    assert tex.shape == (1, 3, res, res) and raw.shape == (res * res, 3)
+    t32, r32 = orc.texture_map(params, res)
+    pr = {k: t.clone().requires_grad_(True) for k, t in params.items()}
+    t16, r16 = orc.texture_map(pr, res, bf16_operands=True)
+    _check(raw.detach(), r32, r16.detach(), f"texture map raw res={res}")
+    et = (tex.detach().cpu() - t16.detach()).abs().max().item()
+    _diag(f"texture map res={res}: max |tex - oracle| {et:.3e}")
+    assert et < 2e-2      # north_star bf16-MLP tolerance (tanh'/2 <= 0.5 halves the raw error)
+    assert tex.min().item() >= 0.0 and tex.max().item() <= 1.0
+    g = torch.Generator().manual_seed(res)
+    gt = torch.randn(1, 3, res, res, generator=g) / (res * res)
+    gr = torch.randn(res * res, 3, generator=g) / (res * res)
+    ((t16 * gt).sum() + (r16 * gr).sum()).backward()
+    ((tex * gt.to(cuda)).sum() + (raw * gr.to(cuda)).sum()).backward()
+    for (name, p) in net.named_parameters():
+        ref = pr[name].grad
+        scale = ref.abs().max().item() + 1e-12
+        l2 = ((p.grad.cpu() - ref).norm() / (ref.norm() + 1e-12)).item()
+        mx = (p.grad.cpu() - ref).abs().max().item() / scale
+        _diag(f"texture map grad {name}: l2 {l2:.3e} max {mx:.3e}")
+        assert l2 < 2e-2 and mx < 4e-2, name
+    # no-grad path saves nothing and matches
+    with torch.no_grad():
+        tex2, raw2 = get_texture_map(net, res)
+    assert torch.equal(tex2, tex.detach())

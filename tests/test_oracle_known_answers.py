@@ -111,3 +111,16 @@ def test_stratified_bounds():
     z = orc.stratified_z(near, far, 64, jitter=j)
     mids = 0.5 * (z0[:, 1:] + z0[:, :-1])
     assert (z[:, 1:-1] >= mids[:, :-1]).all() and (z[:, 1:-1] <= mids[:, 1:]).all()
+
+
+def test_texture_uv_grid_ordering():
+    """'xy' meshgrid: u varies fastest (columns), v along rows; end points exact (textured_mesh.py:268-272)."""
+    g = orc.texture_uv_grid(5)
+    assert g.shape == (25, 2)
+    assert g[0].tolist() == [0.0, 0.0] and g[4].tolist() == [1.0, 0.0]
+    assert g[5].tolist() == [0.0, 0.25] and g[24].tolist() == [1.0, 1.0]
+    torch.manual_seed(0)
+    p = orc.init_mlp_params(42, 3, W=32)
+    tex, raw = orc.texture_map(p, 8)
+    assert tex.shape == (1, 3, 8, 8) and raw.shape == (64, 3)
+    assert torch.allclose(tex[0, :, 2, 3], (torch.tanh(raw[2 * 8 + 3]) + 1) / 2)
