@@ -34,7 +34,7 @@ struct DgradArgs {
 };
 
 struct __align__(8) DgSmemCtl {
-  uint64_t full[kDgPairs], empty[kDgPairs], peer_full[kDgPairs];
+  uint64_t full[kDgPairs], empty[kDgPairs];
   uint64_t acc_full[kTiles], act_ready[kTiles];
   uint32_t tmem_base;
 };
@@ -58,7 +58,7 @@ mlp_dgrad_kernel(const __grid_constant__ DgradArgs a) {
 
   if (tid == 0) {
     for (int s = 0; s < kDgPairs; ++s) {
-      tc::mbar_init(&ctl->full[s], 1); tc::mbar_init(&ctl->empty[s], 1); tc::mbar_init(&ctl->peer_full[s], 1);
+      tc::mbar_init(&ctl->full[s], r == 0 ? 2 : 1); tc::mbar_init(&ctl->empty[s], 1);   // leader: + peer relay
     }
     for (int t = 0; t < kTiles; ++t) { tc::mbar_init(&ctl->acc_full[t], 1); tc::mbar_init(&ctl->act_ready[t], 16); }
     tc::mbar_fence_init();
@@ -107,7 +107,7 @@ mlp_dgrad_kernel(const __grid_constant__ DgradArgs a) {
             if (g & 1) {
               const int pr = (g % kDgStages) >> 1;
               tc::mbar_wait(&ctl->full[pr], (g / kDgStages) & 1);
-              if (tc::elect_one()) tc::mbar_arrive_remote(&ctl->peer_full[pr], 0);
+              if (tc::elect_one()) tc::mbar_arrive_remote(&ctl->full[pr], 0);
               __syncwarp();
             }
           }
@@ -117,42 +117,45 @@ mlp_dgrad_kernel(const __grid_constant__ DgradArgs a) {
       // ============ leader CTA: two MMA issuers, warp 1 -> tile pair A, warp 10 -> tile pair B ============
       // (one thread cannot issue fast enough to keep the tensor pipe fed; see mlp_fwd.cu)
       const int ph = warp == 1 ? 0 : 1;
-      uint32_t gl = 0, act_phase = 0;
-      const uint32_t idesc = tc::make_idesc_bf16(256, 256, 0, 0);
-      const uint32_t h_base = tc::smem_u32(h_buf + ph * kHBytes);
-      const uint32_t acc = tmem + ph * CTX_MLP_W;
-      for (int64_t it = cid; it < n_citers; it += ncl) {
-        for (int si = 0; si < n_steps; ++si) {
-          const int nchunks = net.L[a.step_src[si]].N / CTX_MLP_KC;   // 4 or 8: phases are whole chunk pairs
-          uint32_t g = gl + ph * nchunks;
-          gl += 2 * nchunks;
-          tc::mbar_wait(&ctl->act_ready[ph], act_phase);
-          act_phase ^= 1;
-          tc::tc_fence_after();
-          for (int c = 0; c < nchunks; ++c, ++g) {
-            const int s = g % kDgStages, pr = s >> 1;
-            if (!(g & 1)) {
-              const uint32_t par = (g / kDgStages) & 1;
-              tc::mbar_wait(&ctl->full[pr], par);
-              tc::mbar_wait(&ctl->peer_full[pr], par);
-              tc::tc_fence_after();
-            }
-            const uint32_t a_base = h_base + c * 4 * kK8Stride;
-            const uint32_t b_base = tc::smem_u32(w_buf + s * kDgStageBytes);
-            if (tc::elect_one()) {
+      if (tc::elect_one()) {
+        // single issuing thread, descriptor lo words advanced by adds, one barrier wait + one commit per ring
+        // pair (4 MMAs) -- see mlp_fwd.cu
+        constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);
+        constexpr uint32_t kALbo = (uint32_t)(kK8Stride >> 4) << 16, kBLbo = (2048u >> 4) << 16;
+        constexpr uint32_t kAStep = 4 * kK8Stride >> 4;
+        const uint32_t idesc = tc::make_idesc_bf16(256, 256, 0, 0);
+        const uint32_t h_lo = kALbo | (tc::smem_u32(h_buf + ph * kHBytes) >> 4);
+        const uint32_t w_lo = kBLbo | (tc::smem_u32(w_buf) >> 4);
+        const uint32_t full0 = tc::smem_u32(&ctl->full[0]), empty0 = tc::smem_u32(&ctl->empty[0]);
+        const uint32_t accf = tc::smem_u32(&ctl->acc_full[ph]), actr = tc::smem_u32(&ctl->act_ready[ph]);
+        const uint32_t acc = tmem + ph * CTX_MLP_W;
+        uint32_t gl = 0, act_phase = 0;
+        for (int64_t it = cid; it < n_citers; it += ncl) {
+          for (int si = 0; si < n_steps; ++si) {
+            const int nchunks = net.L[a.step_src[si]].N / CTX_MLP_KC;   // 4 or 8: phases are whole chunk pairs
+            uint32_t g = gl + ph * nchunks;
+            gl += 2 * nchunks;
+            tc::mbar_wait_addr(actr, act_phase);
+            act_phase ^= 1;
+            tc::tc_fence_after();
+            for (int c = 0; c < nchunks; c += 2, g += 2) {
+              const uint32_t s = g & (kDgStages - 1);
+              tc::mbar_wait_addr(full0 + (s >> 1) * 8, (g / kDgStages) & 1);   // both halves landed
 #pragma unroll
-              for (int kk = 0; kk < 2; ++kk) {
-                const uint64_t da = tc::make_smem_desc(a_base + kk * 2 * kK8Stride, kK8Stride, 128);
-                const uint64_t db = tc::make_smem_desc(b_base + kk * 2 * 2048, 2048, 128);
-                tc::mma2_bf16_ss(acc, da, db, idesc, (c > 0 || kk > 0) ? 1u : 0u);
+              for (int j = 0; j < 2; ++j) {
+                const uint32_t a_lo = h_lo + (c + j) * kAStep;
+                const uint32_t b_lo = w_lo + (s + j) * (kDgStageBytes >> 4);
+                tc::mma2_bf16_ss_w(acc, a_lo, kDescHi, b_lo, kDescHi, idesc, (c + j) > 0 ? 1u : 0u);
+                tc::mma2_bf16_ss_w(acc, a_lo + (2 * kK8Stride >> 4), kDescHi, b_lo + (2 * 2048 >> 4), kDescHi, idesc,
+                                   1u);
               }
-              if (c == nchunks - 1) tc::mma2_commit(&ctl->acc_full[ph]);
-              if (g & 1) tc::mma2_commit(&ctl->empty[pr]);
+              if (c + 2 >= nchunks) tc::mma2_commit_addr(accf);
+              tc::mma2_commit_addr(empty0 + (s >> 1) * 8);
             }
-            __syncwarp();
           }
         }
       }
+      __syncwarp();
     }
   } else if (warp >= 2 && warp <= 9) {
     // ============ head-init + epilogue warps ============

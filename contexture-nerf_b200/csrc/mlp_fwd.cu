@@ -33,7 +33,7 @@ constexpr int kHeadFloats = 648;    // view-direction head block staged in share
 constexpr int kStage2Bytes = kStageBytes / 2;   // 8 KB half-chunk
 
 struct __align__(8) Mlp2SmemCtl {
-  uint64_t full[kPairs2], empty[kPairs2], peer_full[kPairs2];
+  uint64_t full[kPairs2], empty[kPairs2];
   uint64_t acc_full[kTiles], act_ready[kTiles];
   uint32_t tmem_base;
 };
@@ -88,7 +88,8 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
 
   if (tid == 0) {
     for (int s = 0; s < kPairs2; ++s) {
-      tc::mbar_init(&ctl->full[s], 1); tc::mbar_init(&ctl->empty[s], 1); tc::mbar_init(&ctl->peer_full[s], 1);
+      // leader: its own producer's arrive + the peer's relay ("my half landed too")
+      tc::mbar_init(&ctl->full[s], r == 0 ? 2 : 1); tc::mbar_init(&ctl->empty[s], 1);
     }
     for (int t = 0; t < kTiles; ++t) { tc::mbar_init(&ctl->acc_full[t], 1); tc::mbar_init(&ctl->act_ready[t], 16); }
     tc::mbar_fence_init();
@@ -149,7 +150,7 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
               if (g & 1) {   // one relay per chunk pair
                 const int pr = (g % kStages2) >> 1;
                 tc::mbar_wait(&ctl->full[pr], (g / kStages2) & 1);
-                if (tc::elect_one()) tc::mbar_arrive_remote(&ctl->peer_full[pr], 0);
+                if (tc::elect_one()) tc::mbar_arrive_remote(&ctl->full[pr], 0);
                 __syncwarp();
               }
             }
@@ -162,64 +163,60 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
         // pipe fed, two threads working on alternate phases can.  Phases are padded to whole chunk pairs so
         // each issuer owns (waits on, commits) complete ring pairs.
         const int ph = warp == 1 ? 0 : 1;
-        uint32_t gl = 0, act_phase = 0;
-        const int dbg = a.debug;
         long long t_act = 0, t_full = 0, t_peer = 0, t_issue = 0;
         const long long t_begin = PCLK();
-        const uint32_t x_base = tc::smem_u32(x_buf + ph * kXBytes), h_base = tc::smem_u32(h_buf + ph * kHBytes);
-        const uint32_t acc = tmem + ph * CTX_MLP_W;
-        for (int64_t it = cid; it < n_citers; it += ncl) {
-          for (int l = 0; l < net.n_layers; ++l) {
-            const int n_x_pre = net.L[l].n_x_pre, n_h = net.L[l].n_h, n_x_post = net.L[l].n_x_post;
-            const int bias_mma = net.L[l].bias_mma, bias_a_off = net.L[l].bias_a_off, LN = net.L[l].N;
-            const int nchunks = n_x_pre + n_h + n_x_post;
-            const int ntot = nchunks + bias_mma, npad = (ntot + 1) & ~1;
-            const uint32_t idesc = tc::make_idesc_bf16(256, LN, 0, 0);
-            const uint32_t b_lbo = (uint32_t)(LN / 2) * 16;
-            uint32_t g = gl + ph * npad;   // this issuer's first chunk of the layer
-            gl += 2 * npad;
-            long long w0 = PCLK();
-            tc::mbar_wait(&ctl->act_ready[ph], act_phase);
-            t_act += PCLK() - w0;
-            act_phase ^= 1;
-            tc::tc_fence_after();
-            for (int c = 0; c < npad; ++c, ++g) {
-              const int s = g % kStages2, pr = s >> 1;
-              if (!(g & 1)) {
-                const uint32_t par = (g / kStages2) & 1;
-                w0 = PCLK();
-                tc::mbar_wait(&ctl->full[pr], par);
-                const long long w1 = PCLK();
-                if (!(dbg & 4)) tc::mbar_wait(&ctl->peer_full[pr], par);
-                const long long w2 = PCLK();
-                t_full += w1 - w0; t_peer += w2 - w1;
-                tc::tc_fence_after();
-              }
-              w0 = PCLK();
-              uint32_t a_base;
-              if (c < n_x_pre) a_base = x_base + c * 4 * kK8Stride;
-              else if (c < n_x_pre + n_h) a_base = h_base + (c - n_x_pre) * 4 * kK8Stride;
-              else if (c < nchunks) a_base = x_base + (c - n_x_pre - n_h) * 4 * kK8Stride;
-              else a_base = x_base + bias_a_off;   // bias chunk: 16 channels ending in the constant 1
-              const uint32_t b_base = tc::smem_u32(w_buf + s * kStage2Bytes);
-              const int nk = c < nchunks ? 2 : (c < ntot ? 1 : 0);   // regular / bias / dummy chunk
-              if (tc::elect_one()) {
+        if (tc::elect_one()) {
+          // One thread runs the whole issue loop (no per-chunk elect / warp sync).  Descriptor hi words are
+          // constants; the lo words (address>>4 | LBO>>4<<16) advance by integer adds.  A ring pair = 2 chunks
+          // = up to 4 MMAs per barrier wait, one commit per pair.
+          constexpr uint32_t kDescHi = (128u >> 4) | (1u << 14);            // SBO = 128 B, descriptor version 1
+          constexpr uint32_t kALbo = (uint32_t)(kK8Stride >> 4) << 16;
+          constexpr uint32_t kAStep = 4 * kK8Stride >> 4;                   // one 32-wide K chunk of an A tile
+          const uint32_t x_lo = kALbo | (tc::smem_u32(x_buf + ph * kXBytes) >> 4);
+          const uint32_t h_lo = kALbo | (tc::smem_u32(h_buf + ph * kHBytes) >> 4);
+          const uint32_t w_lo = tc::smem_u32(w_buf) >> 4;
+          const uint32_t full0 = tc::smem_u32(&ctl->full[0]), empty0 = tc::smem_u32(&ctl->empty[0]);
+          const uint32_t accf = tc::smem_u32(&ctl->acc_full[ph]), actr = tc::smem_u32(&ctl->act_ready[ph]);
+          const uint32_t acc = tmem + ph * CTX_MLP_W;
+          uint32_t gl = 0, act_phase = 0;
+          for (int64_t it = cid; it < n_citers; it += ncl) {
+            for (int l = 0; l < net.n_layers; ++l) {
+              const int n1 = net.L[l].n_x_pre, n2 = n1 + net.L[l].n_h, n3 = n2 + net.L[l].n_x_post;
+              const int ntot = n3 + net.L[l].bias_mma, npad = (ntot + 1) & ~1;
+              const int LN = net.L[l].N;
+              const uint32_t bias_lo = x_lo + ((uint32_t)net.L[l].bias_a_off >> 4);
+              const uint32_t idesc = tc::make_idesc_bf16(256, LN, 0, 0);
+              const uint32_t b_k16 = (uint32_t)LN;                 // 2 * LBO >> 4 : the second 16-wide K half
+              const uint32_t b_lo0 = w_lo | ((uint32_t)(LN / 2) << 16);   // LBO = (N/2) * 16 B
+              uint32_t g = gl + ph * npad;   // this issuer's first chunk of the layer
+              gl += 2 * npad;
+              const long long w0 = PCLK();
+              tc::mbar_wait_addr(actr, act_phase);
+              t_act += PCLK() - w0;
+              act_phase ^= 1;
+              tc::tc_fence_after();
+              for (int c = 0; c < npad; c += 2, g += 2) {
+                const uint32_t s = g & (kStages2 - 1);
+                tc::mbar_wait_addr(full0 + (s >> 1) * 8, (g / kStages2) & 1);   // both halves landed (peer relays)
 #pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                  if (kk < nk && !(dbg & 2)) {
-                    const uint64_t da = tc::make_smem_desc(a_base + kk * 2 * kK8Stride, kK8Stride, 128);
-                    const uint64_t db = tc::make_smem_desc(b_base + kk * 2 * b_lbo, b_lbo, 128);
-                    tc::mma2_bf16_ss(acc, da, db, idesc, (c > 0 || kk > 0) ? 1u : 0u);
-                  }
+                for (int j = 0; j < 2; ++j) {
+                  const int cc = c + j;
+                  const uint32_t a_lo = cc < n1   ? x_lo + cc * kAStep
+                                        : cc < n2 ? h_lo + (cc - n1) * kAStep
+                                        : cc < n3 ? x_lo + (cc - n2) * kAStep
+                                                  : bias_lo;   // 16 channels ending in the constant 1
+                  const uint32_t b_lo = b_lo0 + (s + j) * (kStage2Bytes >> 4);
+                  if (cc < ntot) tc::mma2_bf16_ss_w(acc, a_lo, kDescHi, b_lo, kDescHi, idesc, cc > 0 ? 1u : 0u);
+                  if (cc < n3)
+                    tc::mma2_bf16_ss_w(acc, a_lo + (2 * kK8Stride >> 4), kDescHi, b_lo + b_k16, kDescHi, idesc, 1u);
                 }
-                if (c == ntot - 1) tc::mma2_commit(&ctl->acc_full[ph]);
-                if (g & 1) tc::mma2_commit(&ctl->empty[pr]);
+                if (c + 2 >= ntot) tc::mma2_commit_addr(accf);
+                tc::mma2_commit_addr(empty0 + (s >> 1) * 8);
               }
-              __syncwarp();
-              t_issue += PCLK() - w0;
             }
           }
         }
+        __syncwarp();
         if (kProf && a.prof && lane == 0) {
           unsigned long long* pp = a.prof + blockIdx.x * 16 + (ph ? 0 : 2);
           if (ph == 0) { pp[0] = t_act; pp[1] = t_full; pp[2] = t_peer; pp[7] = t_issue; pp[3] = PCLK() - t_begin; }

@@ -232,7 +232,37 @@ __device__ __forceinline__ void mma2_bf16_ss(uint32_t d_tmem, uint64_t a_desc, u
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same, descriptors passed as (lo, hi) words: the hi words are loop constants and the lo words advance by
+// plain 32-bit adds in the issuing thread
+__device__ __forceinline__ void mma2_bf16_ss_w(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                               uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // completion of all prior MMAs of this thread -> one arrive on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void mma2_commit_addr(uint32_t bar_smem_addr) {
+  const uint16_t mask = 3;
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          bar_smem_addr),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_smem_addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra WAIT_%=;\n\t}" ::"r"(bar_smem_addr),
+      "r"(parity)
+      : "memory");
+}
 __device__ __forceinline__ void mma2_commit(uint64_t* bar) {
   const uint16_t mask = 3;
   asm volatile(

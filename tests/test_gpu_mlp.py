@@ -211,11 +211,11 @@ def test_fused_texture_map_forward_and_backward(cuda, res):
     _diag(f"texture map res={res}: max |tex - oracle| {et:.3e}")
     assert et < 2e-2      # north_star bf16-MLP tolerance (tanh'/2 <= 0.5 halves the raw error)
     assert tex.min().item() >= 0.0 and tex.max().item() <= 1.0
-    g = torch.Generator().manual_seed(res)
-    gt = torch.randn(1, 3, res, res, generator=g) / (res * res)
-    gr = torch.randn(res * res, 3, generator=g) / (res * res)
-    ((t16 * gt).sum() + (r16 * gr).sum()).backward()
-    ((tex * gt.to(cuda)).sum() + (raw * gr.to(cuda)).sum()).backward()
+    # a coherent loss (image MSE against a flat target + a small penalty on the raw output): with a random-sign
+    # g_out the summed gradients cancel to ~1/sqrt(P) of their terms and any ReLU gate that flips between the
+    # in-kernel __sinf encoding and the oracle's sincos shows up amplified (see the backward test above)
+    ((t16 - 0.3).pow(2).mean() + 0.1 * r16.pow(2).mean()).backward()
+    ((tex - 0.3).pow(2).mean() + 0.1 * raw.pow(2).mean()).backward()
     for (name, p) in net.named_parameters():
         ref = pr[name].grad
         scale = ref.abs().max().item() + 1e-12

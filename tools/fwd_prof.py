@@ -12,7 +12,9 @@ z = torch.sort(torch.rand(R, S, device=dev) * 4 + 2, -1)[0]
 prof = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
 names = {14: "epi2.ldtm", 15: "epi2.consume", 1: "epi2.emit", 2: "mma.wait_act", 3: "mma.wait_full", 4: "mma.wait_peer", 9: "mma.issue", 5: "mma.total",
          6: "epi2.wait_acc", 7: "epi2.body", 8: "epi2.total", 13: "epi2.encode", 10: "epi9.wait_acc", 11: "epi9.body", 12: "epi9.total"}
-with torch.no_grad():
+TRAIN = "train" in sys.argv
+if TRAIN: sys.argv.remove("train")
+with (torch.enable_grad() if TRAIN else torch.no_grad()):
     for flags in [int(x) for x in (sys.argv[1:] or ["0"])]:
         _lib.lib().ctx_mlp_set_debug(flags)
         for _ in range(2):
