@@ -32,6 +32,7 @@ struct MlpFwdArgs {
   float* out;               // [P, out_ch]
   uint8_t* acts;            // nullable: per-tile activation records (training)
   unsigned long long* prof; // nullable: per-CTA cycle counters (diagnostics), 16 per CTA
+  unsigned long long* hang; // nullable: host-visible buffer for the deadlock reporter (diagnostics)
   int debug;                // diagnostics: 1 = epilogue skips TMEM loads/stores, 2 = issuer skips the MMAs
 };
 

@@ -140,6 +140,10 @@ mlp_dgrad_kernel(const __grid_constant__ DgradArgs a) {
             tc::tc_fence_after();
             for (int c = 0; c < nchunks; c += 2, g += 2) {
               const uint32_t s = g & (kDgStages - 1);
+              // the previous use of this ring pair may be the other issuer's: it must have been consumed before a
+              // parity wait on the full barrier means this use (see mlp_fwd.cu)
+              if (c < kDgStages && g >= kDgStages)
+                tc::mbar_wait_addr(empty0 + (s >> 1) * 8, ((g - kDgStages) / kDgStages) & 1);
               tc::mbar_wait_addr(full0 + (s >> 1) * 8, (g / kDgStages) & 1);   // both halves landed
 #pragma unroll
               for (int j = 0; j < 2; ++j) {
@@ -205,9 +209,9 @@ mlp_dgrad_kernel(const __grid_constant__ DgradArgs a) {
         store_row8(nullptr, row, 8, gv + 8, false, drec + gout_slot, 16);
       }
       const int nw = lastN / 32;
-      const uint32_t* mrow = reinterpret_cast<const uint32_t*>(rec + last_mask) + row * nw;
+      const uint32_t* mrow = reinterpret_cast<const uint32_t*>(rec + last_mask) + row;   // [column block][row]
       for (int cb = 0; cb < nw; ++cb) {
-        const uint32_t neg = __ldg(mrow + cb);
+        const uint32_t neg = __ldg(mrow + cb * kTileM);
         float v[32];
         if (has_views) {
           const float* wr = hw + 260;
@@ -250,30 +254,50 @@ mlp_dgrad_kernel(const __grid_constant__ DgradArgs a) {
           const uint32_t my_acc = tmem + ph * CTX_MLP_W + ((uint32_t)(q * 32) << 16) + hi * 128;
           // this warp's 128 columns: 4 mask words, fetched while the MMAs run
           uint4 mw = make_uint4(0u, 0u, 0u, 0u);
-          if (Drelu) mw = __ldg(reinterpret_cast<const uint4*>(rec + Dmask) + row * 2 + hi);
+          if (Drelu) {
+            const uint32_t* mp = reinterpret_cast<const uint32_t*>(rec + Dmask) + hi * 4 * kTileM + row;
+            mw = make_uint4(__ldg(mp), __ldg(mp + kTileM), __ldg(mp + 2 * kTileM), __ldg(mp + 3 * kTileM));
+          }
           float d_alpha = 0.f;
           if (add_alpha && p < nP) d_alpha = __ldg(a.g_out + p * 4 + 3);
           const uint32_t par = ph ? acc_phase[1] : acc_phase[0];
           tc::mbar_wait(&ctl->acc_full[ph], par);
           if (ph) acc_phase[1] ^= 1; else acc_phase[0] ^= 1;
           tc::tc_fence_after();
+          // straight-line instantiations (alpha-head term / last step)
+          auto run = [&](auto alpha_c, auto next_c) {
+            constexpr bool ALPHA = decltype(alpha_c)::value, NEXT = decltype(next_c)::value;
+            auto process = [&](const uint32_t (&vr)[32], int cbi) {
+              const uint32_t neg = cbi == 0 ? mw.x : cbi == 1 ? mw.y : cbi == 2 ? mw.z : mw.w;
+              const int cb = hi * 4 + cbi;
+              float v[32];
 #pragma unroll
-          for (int cbi = 0; cbi < 4; ++cbi) {
-            uint32_t vr[32];
-            tc::tmem_ld32(my_acc + cbi * 32, vr);
-            tc::tmem_wait_ld();
-            const uint32_t neg = cbi == 0 ? mw.x : cbi == 1 ? mw.y : cbi == 2 ? mw.z : mw.w;
-            const int cb = hi * 4 + cbi;
-            float v[32];
+              for (int j = 0; j < 32; ++j) {
+                float x = __uint_as_float(vr[j]);
+                if constexpr (ALPHA) x = fmaf(d_alpha, hw[cb * 32 + j], x);
+                v[j] = ((neg >> (31 - j)) & 1u) ? 0.f : x;
+              }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = __uint_as_float(vr[j]);
-              if (add_alpha) x = fmaf(d_alpha, hw[cb * 32 + j], x);
-              v[j] = ((neg >> (31 - j)) & 1u) ? 0.f : x;
+              for (int j = 0; j < 32; j += 8)
+                store_row8(NEXT ? my_h : nullptr, row, cb * 32 + j, v + j, false, drec + Dact, 256);
+            };
+            uint32_t va[32];
+#pragma unroll
+            for (int cbi = 0; cbi < 4; ++cbi) {   // serial load -> wait -> process: running loads ahead measured slower
+              tc::tmem_ld32(my_acc + cbi * 32, va);
+              tc::tmem_wait_ld(va);
+              process(va, cbi);
             }
-#pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              store_row8(has_next ? my_h : nullptr, row, cb * 32 + j, v + j, false, drec + Dact, 256);
+          };
+          {
+            using std::integral_constant;
+            if (add_alpha) {
+              if (has_next) run(integral_constant<bool, true>{}, integral_constant<bool, true>{});
+              else run(integral_constant<bool, true>{}, integral_constant<bool, false>{});
+            } else {
+              if (has_next) run(integral_constant<bool, false>{}, integral_constant<bool, true>{});
+              else run(integral_constant<bool, false>{}, integral_constant<bool, false>{});
+            }
           }
           if (has_next) {
             arrive_act(ph);

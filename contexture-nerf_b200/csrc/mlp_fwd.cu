@@ -68,7 +68,41 @@ __device__ __forceinline__ void encode_row2(uint8_t* tile, int row, const float*
   for (int c0 = 0; c0 < PAD; c0 += 8) store_row8(tile, row, c0, v + c0, false, gtile, PAD);
 }
 
-template <bool kProf>
+// Diagnostics: spin on an mbarrier; when a (pinned, host-visible) buffer is supplied a waiter that has been
+// stuck for ~0.2 s records {tag, block, warp, info, parity} there and traps, so a deadlock names its waiters.
+__device__ __noinline__ void hang_report(unsigned long long* buf, uint32_t tag, uint32_t info, uint32_t parity) {
+  const unsigned long long i = atomicAdd(buf, 1ull);
+  if (i < 60) {
+    unsigned long long* e = buf + 8 + i * 4;
+    e[0] = tag; e[1] = ((unsigned long long)blockIdx.x << 32) | (threadIdx.x >> 5); e[2] = info; e[3] = parity;
+  }
+  __threadfence_system();
+  const long long t0 = clock64();
+  while (clock64() - t0 < 200000000ll) {
+  }
+  __trap();
+}
+template <bool kDiag>
+__device__ __forceinline__ void mbar_wait_dbg(uint32_t addr, uint32_t parity, unsigned long long* buf, uint32_t tag,
+                                              uint32_t info) {
+  if constexpr (!kDiag) {   // production kernels: the plain spin
+    tc::mbar_wait_addr(addr, parity);
+    return;
+  }
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+  if (ok) return;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return;
+    if (buf && clock64() - t0 > 400000000ll) hang_report(buf, tag, info, parity);
+  }
+}
+
+template <bool kProf, bool kRec>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMlpThreads, 1)
 mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
 #define PCLK() (kProf ? clock64() : 0ll)
@@ -123,7 +157,7 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
               const int s = g % kStages2, pr = s >> 1;
               // regular chunk: 32 K ; trailing bias chunk (c == nchunks): 16 K
               const uint32_t bytes = c < nchunks ? half : half / 2;
-              if (!(g & 1)) tc::mbar_wait(&ctl->empty[pr], ((g / kStages2) & 1) ^ 1);
+              if (!(g & 1)) mbar_wait_dbg<kProf>(tc::smem_u32(&ctl->empty[pr]), ((g / kStages2) & 1) ^ 1, a.hang, 1, (uint32_t)(l * 1000 + g % 1000));
               if (tc::elect_one()) {
                 if (c < ntot) {
                   tc::mbar_expect_tx(&ctl->full[pr], bytes);
@@ -149,7 +183,7 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
             for (int c = 0; c < 2 * nchunks; ++c, ++g) {
               if (g & 1) {   // one relay per chunk pair
                 const int pr = (g % kStages2) >> 1;
-                tc::mbar_wait(&ctl->full[pr], (g / kStages2) & 1);
+                mbar_wait_dbg<kProf>(tc::smem_u32(&ctl->full[pr]), (g / kStages2) & 1, a.hang, 2, (uint32_t)(l * 1000 + g % 1000));
                 if (tc::elect_one()) tc::mbar_arrive_remote(&ctl->full[pr], 0);
                 __syncwarp();
               }
@@ -191,13 +225,20 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
               uint32_t g = gl + ph * npad;   // this issuer's first chunk of the layer
               gl += 2 * npad;
               const long long w0 = PCLK();
-              tc::mbar_wait_addr(actr, act_phase);
+              mbar_wait_dbg<kProf>(actr, act_phase, a.hang, 3 + ph * 10, (uint32_t)(l + 100 * (int)((it - cid) / ncl)));
               t_act += PCLK() - w0;
               act_phase ^= 1;
               tc::tc_fence_after();
               for (int c = 0; c < npad; c += 2, g += 2) {
                 const uint32_t s = g & (kStages2 - 1);
-                tc::mbar_wait_addr(full0 + (s >> 1) * 8, (g / kStages2) & 1);   // both halves landed (peer relays)
+                // mbarrier waits only know the phase PARITY.  The previous use of this ring pair may belong to the
+                // other issuer (the first 4 pairs of a layer phase): until that use has been consumed the full
+                // barrier still sits in the older phase and a wait for this one would pass spuriously, so make sure
+                // of it first (own pairs need no check: this thread saw their phase complete before issuing).
+                if (c < kStages2 && g >= kStages2)
+                  mbar_wait_dbg<kProf>(empty0 + (s >> 1) * 8, ((g - kStages2) / kStages2) & 1, a.hang, 6 + ph * 10,
+                                (uint32_t)(l * 1000 + g % 1000));
+                mbar_wait_dbg<kProf>(full0 + (s >> 1) * 8, (g / kStages2) & 1, a.hang, 4 + ph * 10, (uint32_t)(l * 1000 + g % 1000));   // both halves landed (peer relays)
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                   const int cc = c + j;
@@ -229,7 +270,6 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
     const int q = warp & 3;                 // TMEM lane quarter
     const int hi = (warp - 2) >> 2;         // epilogue: column half ; encode: tile (0 = A, 1 = B)
     const int row = q * 32 + lane;
-    const float* fp = a.fparams;
     // head weights: shared memory for the view-direction net, global (L2) for the 4 x 256 output_linear
     const float* hw = net.in_views > 0 ? s_head : a.fparams + net.head_off;
     uint32_t acc_phase[2] = {0, 0};
@@ -307,7 +347,7 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
           uint8_t* my_x = x_buf + ph * kXBytes;
           const uint32_t my_acc = tmem + ph * CTX_MLP_W + ((uint32_t)(q * 32) << 16);
           const long long e0 = PCLK();
-          tc::mbar_wait(&ctl->acc_full[ph], acc_phase[ph]);
+          mbar_wait_dbg<kProf>(tc::smem_u32(&ctl->acc_full[ph]), acc_phase[ph], a.hang, 5 + ph * 10, (uint32_t)(l + 100 * (int)((it - cid) / ncl)));
           const long long e1 = PCLK();
           t_acc += e1 - e0;
           acc_phase[ph] ^= 1;
@@ -315,56 +355,84 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
           float head[4] = {0.f, 0.f, 0.f, 0.f};
           // The bias is already inside the accumulator (constant-1 channel x bias row of the weight stream),
           // so a hidden-layer epilogue is: TMEM load -> (training: sign mask) -> relu+bf16 pack -> store.
-          auto process = [&](const uint32_t (&vr)[32], int cb) {
-            if (rec && Lmask >= 0) {
-              uint32_t neg = 0;   // bit (31-j) = sign of pre-activation j (the ReLU mask the dgrad kernel reads)
+          // One straight-line instantiation per (epilogue kind, relu): the per-block path of a plain hidden
+          // layer is TMEM load -> 16 cvt.relu.bf16x2 -> 4 STS.128 (+ mask word and 4 STG.128 when recording).
+          auto run = [&](auto epi_c, auto relu_c) {
+            constexpr int EPI = decltype(epi_c)::value;
+            constexpr bool RELU = decltype(relu_c)::value;
+            constexpr bool FINAL = (EPI == CTX_EPI_FINAL_VIEWS || EPI == CTX_EPI_FINAL_OUT);
+            uint8_t* const grec = kRec ? rec + Lact : nullptr;
+            auto process = [&](const uint32_t (&vr)[32], int cb) {
+              if constexpr (kRec && RELU) {
+                // bit (31-j) = sign of pre-activation j (the ReLU mask the dgrad kernel reads); four independent
+                // shift chains instead of one 32-deep dependent one
+                uint32_t n0 = 0, n1 = 0, n2 = 0, n3 = 0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) neg = __funnelshift_l(vr[j], neg, 1);
-              reinterpret_cast<uint32_t*>(rec + Lmask)[row * (LN / 32) + cb] = neg;
-            }
-            float v[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(vr[j]);
-            if (Lepi == CTX_EPI_HIDDEN_ALPHA) {
-              float acc = alpha_part[ph];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) acc = fmaf(bf16_round(fmaxf(v[j], 0.f)), hw[cb * 32 + j], acc);
-              alpha_part[ph] = acc;
-            } else if (Lepi == CTX_EPI_FINAL_VIEWS) {
-              const float* wr = hw + 260;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float hv = bf16_round(fmaxf(v[j], 0.f));
-                head[0] = fmaf(hv, wr[cb * 32 + j], head[0]);
-                head[1] = fmaf(hv, wr[128 + cb * 32 + j], head[1]);
-                head[2] = fmaf(hv, wr[256 + cb * 32 + j], head[2]);
+                for (int j = 0; j < 8; ++j) {
+                  n0 = __funnelshift_l(vr[j], n0, 1);
+                  n1 = __funnelshift_l(vr[8 + j], n1, 1);
+                  n2 = __funnelshift_l(vr[16 + j], n2, 1);
+                  n3 = __funnelshift_l(vr[24 + j], n3, 1);
+                }
+                const uint32_t neg = (n0 << 24) | (n1 << 16) | (n2 << 8) | n3;
+                                reinterpret_cast<uint32_t*>(rec + Lmask)[cb * kTileM + row] = neg;   // [column block][row]: coalesced
               }
-            } else if (Lepi == CTX_EPI_FINAL_OUT) {
+              float v[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float hv = bf16_round(fmaxf(v[j], 0.f));
+              for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(vr[j]);
+              if constexpr (EPI == CTX_EPI_HIDDEN_ALPHA) {
+                float acc = alpha_part[ph];
 #pragma unroll
-                for (int o = 0; o < 4; ++o) head[o] = fmaf(hv, hw[o * 256 + cb * 32 + j], head[o]);
+                for (int j = 0; j < 32; ++j) acc = fmaf(bf16_round(fmaxf(v[j], 0.f)), hw[cb * 32 + j], acc);
+                alpha_part[ph] = acc;
+              } else if constexpr (EPI == CTX_EPI_FINAL_VIEWS) {
+                const float* wr = hw + 260;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const float hv = bf16_round(fmaxf(v[j], 0.f));
+                  head[0] = fmaf(hv, wr[cb * 32 + j], head[0]);
+                  head[1] = fmaf(hv, wr[128 + cb * 32 + j], head[1]);
+                  head[2] = fmaf(hv, wr[256 + cb * 32 + j], head[2]);
+                }
+              } else if constexpr (EPI == CTX_EPI_FINAL_OUT) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                  const float hv = bf16_round(fmaxf(v[j], 0.f));
+#pragma unroll
+                  for (int o = 0; o < 4; ++o) head[o] = fmaf(hv, hw[o * 256 + cb * 32 + j], head[o]);
+                }
               }
-            }
-            if (!is_final || rec) {
+              if constexpr (!FINAL || kRec) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 8)
-                store_row8(is_final ? nullptr : my_h, row, cb * 32 + j, v + j, Lrelu != 0,
-                           rec ? rec + Lact : nullptr, LN);
+                for (int j = 0; j < 32; j += 8)
+                  store_row8(FINAL ? nullptr : my_h, row, cb * 32 + j, v + j, RELU, grec, LN);
+              }
+            };
+            uint32_t va[32];
+            const int cb0 = hi * ncb;
+            // (loads are NOT run ahead of the processing: measured slower, with either one or two in flight)
+            for (int cbi = 0; cbi < ncb; ++cbi) {
+              tc::tmem_ld32(my_acc + (cb0 + cbi) * 32, va);
+              tc::tmem_wait_ld(va);
+              process(va, cb0 + cbi);
             }
           };
           if (!(dbg & 1)) {
-            uint32_t va[32], vb[32];
-            const int cb0 = hi * ncb;
-            tc::tmem_ld32(my_acc + cb0 * 32, va);
-            for (int cbi = 0; cbi < ncb; cbi += 2) {     // ncb is 2 or 4; loads run one block ahead
-              tc::tmem_wait_ld();
-              tc::tmem_ld32(my_acc + (cb0 + cbi + 1) * 32, vb);
-              process(va, cb0 + cbi);
-              tc::tmem_wait_ld();
-              if (cbi + 2 < ncb) tc::tmem_ld32(my_acc + (cb0 + cbi + 2) * 32, va);
-              process(vb, cb0 + cbi + 1);
+            using std::integral_constant;
+            switch (Lepi) {
+              case CTX_EPI_HIDDEN:
+                if (Lrelu) run(integral_constant<int, CTX_EPI_HIDDEN>{}, integral_constant<bool, true>{});
+                else run(integral_constant<int, CTX_EPI_HIDDEN>{}, integral_constant<bool, false>{});
+                break;
+              case CTX_EPI_HIDDEN_ALPHA:
+                run(integral_constant<int, CTX_EPI_HIDDEN_ALPHA>{}, integral_constant<bool, true>{});
+                break;
+              case CTX_EPI_FINAL_VIEWS:
+                run(integral_constant<int, CTX_EPI_FINAL_VIEWS>{}, integral_constant<bool, true>{});
+                break;
+              default:
+                run(integral_constant<int, CTX_EPI_FINAL_OUT>{}, integral_constant<bool, true>{});
+                break;
             }
           }
           if (Lepi == CTX_EPI_HIDDEN_ALPHA && hi == 0) {
@@ -440,6 +508,8 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
 // diagnostics: if set (device pointer, 16 x uint64 per CTA), the 2-CTA kernels record where their roles wait
 static void* ctx_mlp_prof_buffer = nullptr;
 static int ctx_mlp_debug_flags = 0;
+static void* ctx_mlp_hang_buffer = nullptr;
+extern "C" int ctx_mlp_set_hang_buffer(void* p) { ctx_mlp_hang_buffer = p; return 0; }
 extern "C" int ctx_mlp_set_debug(int f) { ctx_mlp_debug_flags = f; return 0; }
 extern "C" int ctx_mlp_set_prof_buffer(void* p) { ctx_mlp_prof_buffer = p; return 0; }
 
@@ -467,22 +537,23 @@ extern "C" int ctx_mlp_fwd(const void* net_host, const void* wpacked, const floa
   a.rays_o = rays_o; a.rays_d = rays_d; a.viewdirs = viewdirs; a.z = z; a.S = S; a.L_pts = L_pts;
   a.L_dirs = L_dirs; a.P = P; a.out = out; a.acts = (uint8_t*)acts;
   a.prof = (unsigned long long*)ctx_mlp_prof_buffer; a.debug = ctx_mlp_debug_flags;
+  a.hang = (unsigned long long*)ctx_mlp_hang_buffer;
   cudaStream_t st = (cudaStream_t)stream;
+  using KernelFn = void (*)(ctx::MlpFwdArgs);
+  static const KernelFn kernels[4] = {ctx::mlp_fwd_kernel<false, false>, ctx::mlp_fwd_kernel<false, true>,
+                                      ctx::mlp_fwd_kernel<true, false>, ctx::mlp_fwd_kernel<true, true>};
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(ctx::mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)ctx::kMlp2SmemBytes);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(ctx::mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)ctx::kMlp2SmemBytes);
-    if (e != cudaSuccess) return (int)e;
+    for (KernelFn k : kernels) {
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx::kMlp2SmemBytes);
+      if (e != cudaSuccess) return (int)e;
+    }
     attr_set = true;
   }
   cudaError_t e = cudaMemsetAsync(out, 0, (size_t)P * a.net.out_ch * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
   const int64_t citers = ctx::ceil_div(P, (int64_t)ctx::kTileM * 4);
   const int ncl = (int)(citers < ctx::kNumSMs / 2 ? citers : ctx::kNumSMs / 2);
-  if (a.prof) ctx::mlp_fwd_kernel<true><<<2 * ncl, ctx::kMlpThreads, ctx::kMlp2SmemBytes, st>>>(a);
-  else ctx::mlp_fwd_kernel<false><<<2 * ncl, ctx::kMlpThreads, ctx::kMlp2SmemBytes, st>>>(a);
+  kernels[(a.prof ? 2 : 0) + (a.acts ? 1 : 0)]<<<2 * ncl, ctx::kMlpThreads, ctx::kMlp2SmemBytes, st>>>(a);
   CTX_RETURN_LAST();
 }

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const __grid_c
 #pragma unroll
             for (int j = 16; j < 32; ++j) vr[j] = 0u;
           }
-          tc::tmem_wait_ld();
+          tc::tmem_wait_ld(vr);
           if (m < J.m_valid) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {

@@ -79,7 +79,7 @@ tc_selftest_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __r
   for (int c0 = 0; c0 < N; c0 += 32) {
     uint32_t v[32];
     tc::tmem_ld32(tm + ((uint32_t)(warp * 32) << 16) + c0, v);
-    tc::tmem_wait_ld();
+    tc::tmem_wait_ld(v);
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (c0 + j < N) C[(size_t)row * N + c0 + j] = __uint_as_float(v[j]);
@@ -135,7 +135,7 @@ tc_selftest2_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __
   for (int c0 = 0; c0 < N; c0 += 32) {
     uint32_t v[32];
     tc::tmem_ld32(tm + ((uint32_t)(warp * 32) << 16) + c0, v);
-    tc::tmem_wait_ld();
+    tc::tmem_wait_ld(v);
 #pragma unroll
     for (int j = 0; j < 32; ++j)
       if (c0 + j < N) C[(size_t)(r * 128 + row) * N + c0 + j] = __uint_as_float(v[j]);

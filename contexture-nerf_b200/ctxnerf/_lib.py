@@ -11,7 +11,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libctxnerf.so")
+LIB_PATH = os.environ.get("CTXNERF_LIB") or os.path.join(_HERE, "libctxnerf.so")   # override: kernel experiments
 
 _lib = None
 
@@ -41,6 +41,7 @@ _SIGNATURES = {
     "ctx_mlp_fwd": (c_int, [P, P, P, c_int, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int64, P, P, P]),
     "ctx_mlp_set_prof_buffer": (c_int, [P]),
     "ctx_mlp_set_debug": (c_int, [c_int]),
+    "ctx_mlp_set_hang_buffer": (c_int, [P]),
     "ctx_mlp_dgrad": (c_int, [P, P, P, P, P, P, c_int64, P]),
     "ctx_mlp_wgrad": (c_int, [P, P, P, c_int64, P, c_int, P]),
     "ctx_mlp_bwd": (c_int, [P, P, P, P, P, P, c_int64, P, c_int, P]),

@@ -12,6 +12,17 @@ z = torch.sort(torch.rand(R, S, device=dev) * 4 + 2, -1)[0]
 prof = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
 names = {14: "epi2.ldtm", 15: "epi2.consume", 1: "epi2.emit", 2: "mma.wait_act", 3: "mma.wait_full", 4: "mma.wait_peer", 9: "mma.issue", 5: "mma.total",
          6: "epi2.wait_acc", 7: "epi2.body", 8: "epi2.total", 13: "epi2.encode", 10: "epi9.wait_acc", 11: "epi9.body", 12: "epi9.total"}
+hang = torch.zeros(8 + 64 * 4, dtype=torch.int64).pin_memory()
+_lib.lib().ctx_mlp_set_hang_buffer(hang.data_ptr())
+def report():
+    k = int(hang[0])
+    print("HANG REPORT: waiters", k)
+    TAGS = {1: "producer.empty", 2: "relay.full", 3: "issuerA.act", 13: "issuerB.act", 4: "issuerA.full", 14: "issuerB.full",
+            5: "epi.accA", 15: "epi.accB"}
+    for i in range(min(k, 60)):
+        e = hang[8 + 4 * i: 12 + 4 * i].tolist()
+        print("   ", TAGS.get(e[0], e[0]), "block", e[1] >> 32, "warp", e[1] & 0xffffffff, "info", e[2], "parity", e[3])
+import atexit; atexit.register(report)
 TRAIN = "train" in sys.argv
 if TRAIN: sys.argv.remove("train")
 with (torch.enable_grad() if TRAIN else torch.no_grad()):
