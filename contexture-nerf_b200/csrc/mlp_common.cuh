@@ -74,9 +74,9 @@ __device__ __forceinline__ void store_row8(uint8_t* tile, int row, int ch0, cons
     q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
   }
   if (tile) *reinterpret_cast<uint4*>(tile + (ch0 >> 3) * kK8Stride + (row >> 3) * 128 + (row & 7) * 16) = q;
-  if (gtile)
-    *reinterpret_cast<uint4*>(gtile + (row >> 6) * (gC * 128) + (ch0 >> 3) * 1024 + ((row & 63) >> 3) * 128 +
-                              (row & 7) * 16) = q;
+  if (gtile)   // streaming store: the record is next read by another kernel, keep it out of the (small) L1
+    __stcs(reinterpret_cast<uint4*>(gtile + (row >> 6) * (gC * 128) + (ch0 >> 3) * 1024 + ((row & 63) >> 3) * 128 +
+                                    (row & 7) * 16), q);
 }
 
 }  // namespace ctx

@@ -211,7 +211,7 @@ mlp_dgrad_kernel(const __grid_constant__ DgradArgs a) {
       const int nw = lastN / 32;
       const uint32_t* mrow = reinterpret_cast<const uint32_t*>(rec + last_mask) + row;   // [column block][row]
       for (int cb = 0; cb < nw; ++cb) {
-        const uint32_t neg = __ldg(mrow + cb * kTileM);
+        const uint32_t neg = __ldcs(mrow + cb * kTileM);
         float v[32];
         if (has_views) {
           const float* wr = hw + 260;
@@ -256,7 +256,7 @@ mlp_dgrad_kernel(const __grid_constant__ DgradArgs a) {
           uint4 mw = make_uint4(0u, 0u, 0u, 0u);
           if (Drelu) {
             const uint32_t* mp = reinterpret_cast<const uint32_t*>(rec + Dmask) + hi * 4 * kTileM + row;
-            mw = make_uint4(__ldg(mp), __ldg(mp + kTileM), __ldg(mp + 2 * kTileM), __ldg(mp + 3 * kTileM));
+            mw = make_uint4(__ldcs(mp), __ldcs(mp + kTileM), __ldcs(mp + 2 * kTileM), __ldcs(mp + 3 * kTileM));
           }
           float d_alpha = 0.f;
           if (add_alpha && p < nP) d_alpha = __ldg(a.g_out + p * 4 + 3);

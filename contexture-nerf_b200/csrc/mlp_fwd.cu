@@ -375,7 +375,7 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
                   n3 = __funnelshift_l(vr[24 + j], n3, 1);
                 }
                 const uint32_t neg = (n0 << 24) | (n1 << 16) | (n2 << 8) | n3;
-                                reinterpret_cast<uint32_t*>(rec + Lmask)[cb * kTileM + row] = neg;   // [column block][row]: coalesced
+                                __stcs(reinterpret_cast<uint32_t*>(rec + Lmask) + cb * kTileM + row, neg);   // [column block][row]: coalesced
               }
               float v[32];
 #pragma unroll
