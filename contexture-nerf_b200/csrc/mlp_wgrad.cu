@@ -23,11 +23,11 @@ namespace ctx {
 
 // ============================== wgrad ======================================
 // Units of the operand ring are HALF tiles (64 points x channels, <= 32 KB, contiguous in the record);
-// a group = {A half, B half} feeds 4 K16 MMAs per 128-wide M half.  Six 32 KB slots = three groups: one
+// a group = {A half, B half} feeds 4 K16 MMAs per 128-wide M half.  Seven 32 KB slots = three and a half groups: one
 // being consumed, two in flight from HBM, which is what it takes to keep the per-SM share of the HBM
 // bandwidth busy (the kernel is bandwidth-bound: 1 KB per point per layer).
 constexpr int kWgUnitBytes = 32768;
-constexpr int kWgUnits = 6;
+constexpr int kWgUnits = 7;
 constexpr int kWgThreads = 192;     // warp 0 producer, warp 1 MMA, warps 2-5 column sums + flush
 constexpr int kWgMaxJobs = 48;
 constexpr size_t kWgSmemBytes = (size_t)kWgUnits * kWgUnitBytes + 256;
