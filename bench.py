@@ -33,7 +33,9 @@ CONFIG = {"workload": "configs[2]: training step fwd+bwd, 4096-ray batch per GPU
                       "D=8/W=256 view-dir MLPs, L=10/4, gradient all-reduce + Adam",
           "rays_per_gpu": RAYS_PER_GPU, "n_samples": N_SAMPLES, "n_importance": N_IMPORTANCE,
           "image": "800x800 config-2 camera", "perturb": 1.0, "white_bkgd": True,
-          "l2": "no explicit flush: each step streams ~10 GB of activation records through the 126 MB L2"}
+          "l2": "no explicit flush: each step streams ~17 GB of activation / dZ records through the 126 MB L2",
+          "schedule": "backward of the coarse network (dgrad -> wgrad) on a side stream beside wgrad of the fine network "
+                      "(SM budgets 44 / 104); one gradient all-reduce"}
 
 
 def peaks():
@@ -235,10 +237,22 @@ def main():
     e2e = RAYS_PER_GPU * world * args.steps / (ms_e2e * 1e-3)
     final_loss = float(loss_h.item())
 
-    # ---- per-kernel device times inside the timed region -> roofline of the dominant kernel ----
+    # ---- per-kernel device times -> roofline ----
+    # The timed region overlaps the coarse network's backward chain with wgrad of the fine network (side stream,
+    # disjoint SM budgets), so the kernels' own durations are taken in a short extra pass with the overlap off
+    # ("kernels"), and the dominant PHASE of the timed region -- the concurrent group wgrad_fine || dgrad_coarse ->
+    # wgrad_coarse, timed live with events on the main stream -- is what "roofline" reports.
     pk = peaks()
+    group_ms = None
+    if timers and "bwd_overlap_group" in timers:
+        evs = timers["bwd_overlap_group"]
+        group_ms = sum(x.elapsed_time(y) for x, y in evs) / len(evs)
+    overlap_was = tr.overlap_backward
+    tr.overlap_backward = False
+    _, _, _, timers_iso = timed(lambda i: tr.step(idx_d[i % NB], tgt_d[i % NB]), min(args.steps, 6), True)
+    tr.overlap_backward = overlap_was
     kern = {}
-    for name, evs in (timers or {}).items():
+    for name, evs in (timers_iso or {}).items():
         kern[name] = sum(x.elapsed_time(y) for x, y in evs) / len(evs)
     pts = {"coarse": RAYS_PER_GPU * N_SAMPLES, "fine": RAYS_PER_GPU * (N_SAMPLES + N_IMPORTANCE)}
     # records per point of the view-direction net: bf16 activations of the 10 GEMM layers
@@ -272,12 +286,24 @@ def main():
             else:
                 kernels[name] = {"bound": "hbm", "achieved": gb, "peak": pk["hbm_gbs"], "unit": "GB/s",
                                  "frac": f_h, "ms_per_launch": t_ms, "tensor_tflops": tf, "tensor_frac": f_t}
-    dom = max(kern, key=kern.get) if kern else None
     roofline = None
-    if dom:
-        roofline = dict(kernels[dom], kernel=dom, traffic=traffic.get(dom),
-                        peak_source=pk["source"] + (" copy bandwidth" if kernels[dom]["bound"] == "hbm"
-                                                    else " cuBLAS bf16, sustained"))
+    if group_ms is not None:
+        gbytes = (WGRAD_BYTES_PER_POINT * pts["fine"] + (REC_BYTES_PER_POINT["dgrad"] + WGRAD_BYTES_PER_POINT) * pts["coarse"])
+        gtraffic = None
+        if all(k in traffic for k in ("mlp_wgrad_fine", "mlp_dgrad_coarse", "mlp_wgrad_coarse")):
+            gtraffic = traffic["mlp_wgrad_fine"] + traffic["mlp_dgrad_coarse"] + traffic["mlp_wgrad_coarse"]
+        ach = gbytes / (group_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
+                    "traffic": gtraffic, "ms_per_launch": group_ms,
+                    "kernel": "mlp_wgrad_fine || (mlp_dgrad_coarse -> mlp_wgrad_coarse): concurrent on disjoint SM budgets, "
+                              "timed as one span on the main stream; per-kernel figures (overlap off) under 'kernels'",
+                    "peak_source": pk["source"] + " copy bandwidth"}
+    else:
+        dom = max(kern, key=kern.get) if kern else None
+        if dom:
+            roofline = dict(kernels[dom], kernel=dom, traffic=traffic.get(dom),
+                            peak_source=pk["source"] + (" copy bandwidth" if kernels[dom]["bound"] == "hbm"
+                                                        else " cuBLAS bf16, sustained"))
     step_flops = 3 * 2.0 * MACS_PER_EVAL * RAYS_PER_GPU * EVALS_PER_RAY
     line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

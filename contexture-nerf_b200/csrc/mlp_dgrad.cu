@@ -324,7 +324,7 @@ mlp_dgrad_kernel(const __grid_constant__ DgradArgs a) {
 
 // host launcher used by ctx_mlp_bwd (mlp_wgrad.cu)
 int ctx_launch_dgrad(const CtxMlpNet& net, const void* wtpacked, const float* fparams, const float* g_out,
-                      const void* acts, void* dacts, int64_t P, cudaStream_t st) {
+                      const void* acts, void* dacts, int64_t P, int max_sms, cudaStream_t st) {
   ctx::DgradArgs a;
   a.net = net;
   a.wtstream = (const uint8_t*)wtpacked;
@@ -340,7 +340,10 @@ int ctx_launch_dgrad(const CtxMlpNet& net, const void* wtpacked, const float* fp
     attr_set = true;
   }
   const int64_t citers = ctx::ceil_div(P, (int64_t)ctx::kTileM * 4);
-  const int ncl = (int)(citers < ctx::kNumSMs / 2 ? citers : ctx::kNumSMs / 2);
+  int cap = ctx::kNumSMs / 2;   // one cluster per SM pair; a smaller SM budget leaves room for a concurrent kernel
+  if (max_sms > 0 && max_sms / 2 < cap) cap = max_sms / 2;
+  if (cap < 1) cap = 1;
+  const int ncl = (int)(citers < cap ? citers : cap);
   ctx::mlp_dgrad_kernel<<<2 * ncl, ctx::kMlpThreads, ctx::kDgSmemBytes, st>>>(a);
   return (int)cudaGetLastError();
 }

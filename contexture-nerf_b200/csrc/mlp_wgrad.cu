@@ -17,7 +17,7 @@
 
 // dgrad kernel launcher (mlp_dgrad.cu)
 int ctx_launch_dgrad(const CtxMlpNet& net, const void* wtpacked, const float* fparams, const float* g_out,
-                      const void* acts, void* dacts, int64_t P, cudaStream_t st);
+                      const void* acts, void* dacts, int64_t P, int max_sms, cudaStream_t st);
 
 namespace ctx {
 
@@ -232,8 +232,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const __grid_c
 
 // grads: HOST array of DEVICE pointers in the order of ctx_mlp_pack's `params`
 // (gradients are ACCUMULATED into them: zero them first for a fresh gradient).
-extern "C" int ctx_mlp_wgrad(const void* net_host, const void* acts, const void* dacts, int64_t P,
-                             float* const* grads, int n_grads, void* stream) {
+// max_sms > 0: use at most that many CTAs (rounded down to even) and launch them as 2-CTA clusters, so that they
+// pack into whole SM pairs and a concurrent cluster kernel (dgrad of the other network) finds free pairs.
+extern "C" int ctx_mlp_wgrad_ex(const void* net_host, const void* acts, const void* dacts, int64_t P,
+                                float* const* grads, int n_grads, int max_sms, void* stream) {
   if (!net_host || !acts || !dacts || !grads || P < 0) return CTX_ERR_BAD_ARG;
   if (P == 0) return 0;
   const CtxMlpNet& net = *reinterpret_cast<const CtxMlpNet*>(net_host);
@@ -307,7 +309,9 @@ extern "C" int ctx_mlp_wgrad(const void* net_host, const void* acts, const void*
     float total = 0.f;
     for (int j = 0; j < nj; ++j) total += cost[j];
     int budget = ctx::kNumSMs, begin = 0;
-    if (budget < nj) return CTX_ERR_UNSUPPORTED;
+    const bool capped = max_sms > 0 && max_sms < ctx::kNumSMs;
+    if (capped) budget = max_sms & ~1;
+    if (budget < 2 * nj) return CTX_ERR_UNSUPPORTED;
     int given[ctx::kWgMaxJobs];
     int used = 0;
     for (int j = 0; j < nj; ++j) {
@@ -322,17 +326,39 @@ extern "C" int ctx_mlp_wgrad(const void* net_host, const void* acts, const void*
     }
     for (int j = 0; j < nj; ++j) { w.job[j].cta_begin = begin; w.job[j].cta_count = given[j]; begin += given[j]; }
     w.n_jobs = nj;
-    ctx::mlp_wgrad_kernel<<<begin, ctx::kWgThreads, ctx::kWgSmemBytes, st>>>(w);
+    if (capped && (begin & 1) == 0) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(begin); cfg.blockDim = dim3(ctx::kWgThreads); cfg.dynamicSmemBytes = ctx::kWgSmemBytes;
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      cudaError_t e = cudaLaunchKernelEx(&cfg, ctx::mlp_wgrad_kernel, w);
+      if (e != cudaSuccess) return (int)e;
+    } else {
+      ctx::mlp_wgrad_kernel<<<begin, ctx::kWgThreads, ctx::kWgSmemBytes, st>>>(w);
+    }
   }
   CTX_RETURN_LAST();
 }
 
-extern "C" int ctx_mlp_dgrad(const void* net_host, const void* wtpacked, const float* fparams, const float* g_out,
-                             const void* acts, void* dacts, int64_t P, void* stream) {
+extern "C" int ctx_mlp_wgrad(const void* net_host, const void* acts, const void* dacts, int64_t P,
+                             float* const* grads, int n_grads, void* stream) {
+  return ctx_mlp_wgrad_ex(net_host, acts, dacts, P, grads, n_grads, 0, stream);
+}
+
+extern "C" int ctx_mlp_dgrad_ex(const void* net_host, const void* wtpacked, const float* fparams, const float* g_out,
+                                const void* acts, void* dacts, int64_t P, int max_sms, void* stream) {
   if (!net_host || !wtpacked || !fparams || !g_out || !acts || !dacts || P < 0) return CTX_ERR_BAD_ARG;
   if (P == 0) return 0;
   return ctx_launch_dgrad(*reinterpret_cast<const CtxMlpNet*>(net_host), wtpacked, fparams, g_out, acts, dacts, P,
-                          (cudaStream_t)stream);
+                          max_sms, (cudaStream_t)stream);
+}
+
+extern "C" int ctx_mlp_dgrad(const void* net_host, const void* wtpacked, const float* fparams, const float* g_out,
+                             const void* acts, void* dacts, int64_t P, void* stream) {
+  return ctx_mlp_dgrad_ex(net_host, wtpacked, fparams, g_out, acts, dacts, P, 0, stream);
 }
 
 extern "C" int ctx_mlp_bwd(const void* net_host, const void* wtpacked, const float* fparams,

@@ -13,13 +13,15 @@ from __future__ import annotations
 import ctypes
 from typing import Optional
 
+import os
+
 import torch
 
 from . import ops
 from ._lib import call, ptr, stream_ptr
 from .dist import FlatBucket, world
 from .mlp import forward_raw
-from .mlp_bwd import mlp_backward
+from .mlp_bwd import mlp_backward, mlp_dgrad, mlp_wgrad
 from .run_nerf_helpers import NeRF
 
 
@@ -51,6 +53,11 @@ class NerfTrainer:
         self.rank, self.world_size = world()
         self._loss = torch.zeros(1, device=self.device)
         self.timers = None      # optional dict name -> list[(start_event, end_event)]
+        # backward overlap (see step): side stream + SM budget of the coarse chain
+        self.overlap_backward = os.environ.get("CTXNERF_OVERLAP", "1") != "0"
+        self.side_sms = int(os.environ.get("CTXNERF_SIDE_SMS", "44"))
+        self._side = torch.cuda.Stream(device=self.device)
+        self._ev0, self._ev1 = torch.cuda.Event(), torch.cuda.Event()
 
     # ------------------------------------------------------------------ utils
     def _timed(self, name, fn):
@@ -134,12 +141,41 @@ class NerfTrainer:
             call("ctx_mse_fwd_bwd", ptr(f["comp_f"][0]), ptr(f["comp_c"][0]), ptr(target), R * 3, 1.0,
                  ptr(self._loss), ptr(g_rgb), ptr(g_rgb0), stream_ptr(dev))
             g_raw_f = self._composite_bwd(f["raw_f"], f["z_f"], f["d"], R, Sf, g_rgb)
-            mlp_backward(self.fine, f["pk_f"], f["acts_f"], f["Pf"], g_raw_f, sinks=self.bucket.sinks_for(self.fine),
-                         timed=lambda n, fn: self._timed(f"mlp_{n}_fine", fn))
             g_raw_c = self._composite_bwd(f["raw_c"], f["z_c"], f["d"], R, S, g_rgb0)
-            mlp_backward(self.coarse, f["pk_c"], f["acts_c"], f["Pc"], g_raw_c,
-                         sinks=self.bucket.sinks_for(self.coarse),
-                         timed=lambda n, fn: self._timed(f"mlp_{n}_coarse", fn))
+            sinks_f, sinks_c = self.bucket.sinks_for(self.fine), self.bucket.sinks_for(self.coarse)
+            dacts_f = self._timed("mlp_dgrad_fine",
+                                  lambda: mlp_dgrad(self.fine, f["pk_f"], f["acts_f"], f["Pf"], g_raw_f))
+            if self.overlap_backward:
+                # The two networks' backward chains are independent, and their kernels bind on different
+                # resources: dgrad on the tensor pipe / epilogue, wgrad on HBM reads.  The coarse chain runs on a
+                # side stream inside a 36-SM budget while wgrad of the fine network streams its records through
+                # the other 112 SMs; wgrad of the coarse network follows on whatever SMs come free.
+                main = torch.cuda.current_stream(dev)
+                self._ev0.record(main)
+                self._side.wait_event(self._ev0)
+                if self.timers is not None:
+                    g0 = torch.cuda.Event(enable_timing=True)
+                    g0.record(main)
+                with torch.cuda.stream(self._side):
+                    dacts_c = self._timed("mlp_dgrad_coarse",
+                                          lambda: mlp_dgrad(self.coarse, f["pk_c"], f["acts_c"], f["Pc"], g_raw_c,
+                                                            max_sms=self.side_sms))
+                    self._timed("mlp_wgrad_coarse",
+                                lambda: mlp_wgrad(self.coarse, f["acts_c"], dacts_c, f["Pc"], sinks_c))
+                    self._ev1.record(self._side)
+                self._timed("mlp_wgrad_fine",
+                            lambda: mlp_wgrad(self.fine, f["acts_f"], dacts_f, f["Pf"], sinks_f,
+                                              max_sms=148 - self.side_sms))
+                main.wait_event(self._ev1)
+                if self.timers is not None:   # span of the concurrent group on the main stream
+                    g1 = torch.cuda.Event(enable_timing=True)
+                    g1.record(main)
+                    self.timers.setdefault("bwd_overlap_group", []).append((g0, g1))
+            else:
+                self._timed("mlp_wgrad_fine", lambda: mlp_wgrad(self.fine, f["acts_f"], dacts_f, f["Pf"], sinks_f))
+                dacts_c = self._timed("mlp_dgrad_coarse",
+                                      lambda: mlp_dgrad(self.coarse, f["pk_c"], f["acts_c"], f["Pc"], g_raw_c))
+                self._timed("mlp_wgrad_coarse", lambda: mlp_wgrad(self.coarse, f["acts_c"], dacts_c, f["Pc"], sinks_c))
             self.bucket.all_reduce()
             if optimizer_step:
                 self.step_count += 1

@@ -140,6 +140,13 @@ int ctx_mlp_dgrad(const void* net, const void* wtpacked, const float* fparams, c
                   const void* acts, void* dacts, int64_t P, void* stream);
 int ctx_mlp_wgrad(const void* net, const void* acts, const void* dacts, int64_t P, float* const* grads,
                   int n_grads, void* stream);
+/* the same with an SM budget (max_sms > 0: at most that many SMs are occupied; 0 = the whole GPU), so that the
+ * tensor-bound dgrad of one network can run beside the HBM-bound wgrad of the other on disjoint SM pairs
+ * (NerfTrainer.step: dgrad_coarse || wgrad_fine).                                                         */
+int ctx_mlp_dgrad_ex(const void* net, const void* wtpacked, const float* fparams, const float* g_out,
+                     const void* acts, void* dacts, int64_t P, int max_sms, void* stream);
+int ctx_mlp_wgrad_ex(const void* net, const void* acts, const void* dacts, int64_t P, float* const* grads,
+                     int n_grads, int max_sms, void* stream);
 
 /* ---- fused texture map: get_texture_map, src/models/textured_mesh.py:266-301 -----------------------
  * ctx_mlp_fwd mode 2 generates the res x res UV grid (meshgrid of linspace(0,1,res), 'xy' indexing, :269-272),
