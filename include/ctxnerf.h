@@ -142,7 +142,8 @@ int ctx_mlp_wgrad(const void* net, const void* acts, const void* dacts, int64_t 
                   int n_grads, void* stream);
 /* the same with an SM budget (max_sms > 0: at most that many SMs are occupied; 0 = the whole GPU), so that the
  * tensor-bound dgrad of one network can run beside the HBM-bound wgrad of the other on disjoint SM pairs
- * (NerfTrainer.step: dgrad_coarse || wgrad_fine).                                                         */
+ * (NerfTrainer.step: dgrad_coarse || wgrad_fine).  dgrad accepts any budget >= 2 (one cluster); wgrad needs two
+ * SMs per (layer, segment) job -- 28 for the view-direction net -- and returns CTX_ERR_UNSUPPORTED below that.  */
 int ctx_mlp_dgrad_ex(const void* net, const void* wtpacked, const float* fparams, const float* g_out,
                      const void* acts, void* dacts, int64_t P, int max_sms, void* stream);
 int ctx_mlp_wgrad_ex(const void* net, const void* acts, const void* dacts, int64_t P, float* const* grads,
