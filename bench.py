@@ -200,11 +200,13 @@ def main():
         if world > 1:
             dist.barrier()
 
-    def timed(step_fn, steps, with_timers):
+    def timed(step_fn, steps, with_timers, after=None):
         cs = ClockSampler(local)
         cs.start()
         for i in range(warm):
             step_fn(i)
+        if after is not None:
+            after()
         torch.cuda.synchronize()
         cs.wait_first_sample()
         barrier()
@@ -216,6 +218,8 @@ def main():
         a.record()
         for i in range(steps):
             step_fn(warm + i)
+        if after is not None:
+            after()          # the last step's loss is read inside the timed region too
         b.record()
         torch.cuda.synchronize()
         clocks = cs.stop()
@@ -232,10 +236,31 @@ def main():
     ms, clocks, launches, timers = timed(lambda i: tr.step(idx_d[i % NB], tgt_d[i % NB]), args.steps, True)
     value = RAYS_PER_GPU * world * args.steps / (ms * 1e-3)
     # ---- end to end through the public API with host buffers ----
-    ms_e2e, _, _, _ = timed(lambda i: (tr.step_from_host(idx_h[i % NB], tgt_h[i % NB], loss_h), torch.cuda.current_stream().synchronize()),
-                            args.steps, False)
+    # Every step copies its ray ids + targets from pinned host memory and its loss is read on the host; the host
+    # reads the loss of step i after it has submitted step i+1 (two pinned loss slots), as a training loop that logs
+    # the loss does, so the submission of the next step is not exposed between steps.
+    loss_slots = [torch.zeros(1).pin_memory(), torch.zeros(1).pin_memory()]
+    pending = []
+    host_losses = []
+
+    def e2e_step(i):
+        ev = tr.step_from_host(idx_h[i % NB], tgt_h[i % NB], loss_slots[i & 1])
+        if pending:
+            pev, slot = pending.pop()
+            pev.synchronize()
+            host_losses.append(float(slot.item()))
+        pending.append((ev, loss_slots[i & 1]))
+
+    def e2e_drain():
+        while pending:
+            pev, slot = pending.pop()
+            pev.synchronize()
+            host_losses.append(float(slot.item()))
+
+    ms_e2e, _, _, _ = timed(e2e_step, args.steps, False, after=e2e_drain)
     e2e = RAYS_PER_GPU * world * args.steps / (ms_e2e * 1e-3)
-    final_loss = float(loss_h.item())
+    final_loss = host_losses[-1]
+    loss_h.fill_(final_loss)
 
     # ---- per-kernel device times -> roofline ----
     # The timed region overlaps the coarse network's backward chain with wgrad of the fine network (side stream,

@@ -187,9 +187,14 @@ class NerfTrainer:
         return self._loss
 
     def step_from_host(self, ray_idx_pinned: torch.Tensor, target_pinned: torch.Tensor,
-                       loss_pinned: torch.Tensor) -> None:
-        """End-to-end entry: host (pinned) inputs in, loss back to the host."""
+                       loss_pinned: torch.Tensor) -> "torch.cuda.Event":
+        """End-to-end entry: host (pinned) inputs in, loss back to the host.  Asynchronous: the returned event marks
+        the arrival of the loss in ``loss_pinned``, so a training loop can submit step i+1 before it reads the loss
+        of step i (the launches of the next step then hide behind the GPU work of this one)."""
         idx = ray_idx_pinned.to(self.device, non_blocking=True)
         tgt = target_pinned.to(self.device, non_blocking=True)
         loss = self.step(idx, tgt)
         loss_pinned.copy_(loss, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(torch.cuda.current_stream(self.device))
+        return done     # loss_pinned is valid once this event has completed
