@@ -1,10 +1,11 @@
 // raw2outputs: density -> alpha, exclusive-cumprod transmittance, weighted
-// rgb/depth/acc.  One warp per ray, shuffle scans, 128-bit loads of raw.
+// rgb/depth/acc.  One warp per ray (each lane a block of consecutive samples), shuffle scans, 128-bit loads.
 //
 // Spec: upstream nerf-pytorch raw2outputs as restated in SURVEY.md 8c-S1 (the
 // reference tree only carries the pointer comment, src/run_nerf_helpers.py:131-133).
 // HBM-bound: fwd moves 24*S+36 B/ray, bwd 40*S+36 B/ray.
 #include "ctx_common.cuh"
+#include <initializer_list>
 
 namespace ctx {
 
@@ -34,58 +35,107 @@ __device__ __forceinline__ float warp_scan_prod(float v, int lane) {
   return v;
 }
 
-// CH = number of 32-sample chunks held in registers (S <= 32*CH)
-template <int CH>
+// Blocked sample-to-lane map: lane l owns the K consecutive samples [l*K, l*K+K) (S <= 32*K), so a ray costs ONE
+// warp scan and ONE set of warp reductions whatever its length; the per-sample work is a serial pass over registers.
+// K consecutive floats / float4 per lane keep every global access a whole number of 16- or 32-byte pieces.
+template <int K>
+__device__ __forceinline__ void load_row(const float* __restrict__ p, int64_t base, int s0, int S, int vec,
+                                         float (&v)[K + 1]) {
+  if ((K & 3) == 0 && vec >= 4) {
+#pragma unroll
+    for (int k = 0; k < K; k += 4) {
+      const float4 q = (s0 + k < S) ? __ldg(reinterpret_cast<const float4*>(p + base + s0 + k))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[k] = q.x; v[k + 1] = q.y; v[k + 2] = q.z; v[k + 3] = q.w;
+    }
+  } else if ((K & 1) == 0 && vec >= 2) {
+#pragma unroll
+    for (int k = 0; k < K; k += 2) {
+      const float2 q = (s0 + k < S) ? __ldg(reinterpret_cast<const float2*>(p + base + s0 + k)) : make_float2(0.f, 0.f);
+      v[k] = q.x; v[k + 1] = q.y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = (s0 + k < S) ? __ldg(p + base + s0 + k) : 0.f;
+  }
+}
+template <int K>
+__device__ __forceinline__ void store_row(float* __restrict__ p, int64_t base, int s0, int S, int vec,
+                                          const float (&v)[K]) {
+  if ((K & 3) == 0 && vec >= 4) {
+#pragma unroll
+    for (int k = 0; k < K; k += 4)
+      if (s0 + k < S) *reinterpret_cast<float4*>(p + base + s0 + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+  } else if ((K & 1) == 0 && vec >= 2) {
+#pragma unroll
+    for (int k = 0; k < K; k += 2)
+      if (s0 + k < S) *reinterpret_cast<float2*>(p + base + s0 + k) = make_float2(v[k], v[k + 1]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+      if (s0 + k < S) p[base + s0 + k] = v[k];
+  }
+}
+
+template <int K>
 __global__ void __launch_bounds__(kCompWarps * 32)
 composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z,
                      const float* __restrict__ rays_d, const float* __restrict__ noise,
-                     int64_t R, int S, int white_bkgd,
+                     int64_t R, int S, int vec, int white_bkgd,
                      float* __restrict__ rgb_map, float* __restrict__ disp_map,
                      float* __restrict__ acc_map, float* __restrict__ weights,
                      float* __restrict__ depth_map) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kCompWarps;
+  const int s0 = lane * K;
   for (int64_t ray = warp0; ray < R; ray += nwarps) {
     const float dx = rays_d[ray * 3 + 0], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
     const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
     const int64_t base = ray * S;
-    float4 rw[CH];
-    float zc[CH], zn[CH], nz[CH];
-    // issue every load of the ray up front
+    float4 rw[K];
+    float zl[K + 1], nz[K + 1];
+    // every load of the ray is issued up front
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int s = c * 32 + lane;
-      const bool ok = s < S;
-      rw[c] = ok ? __ldg(raw + base + s) : make_float4(0.f, 0.f, 0.f, 0.f);
-      zc[c] = ok ? __ldg(z + base + s) : 0.f;
-      zn[c] = (s + 1 < S) ? __ldg(z + base + s + 1) : 0.f;
-      nz[c] = (noise != nullptr && ok) ? __ldg(noise + base + s) : 0.f;
+    for (int k = 0; k < K; ++k)
+      rw[k] = (s0 + k < S) ? __ldg(raw + base + s0 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    load_row<K>(z, base, s0, S, vec, zl);
+    if (noise != nullptr) load_row<K>(noise, base, s0, S, vec, nz);
+    else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) nz[k] = 0.f;
     }
-    float carry = 1.0f, sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f;
+    zl[K] = __shfl_down_sync(CTX_FULL_MASK, zl[0], 1);   // first depth of the next lane
+    // serial pass: alpha and the transmittance prefix inside the lane
+    float al[K], pref[K];
+    float run = 1.0f;
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int s = c * 32 + lane;
+    for (int k = 0; k < K; ++k) {
+      const int s = s0 + k;
       const bool ok = s < S;
-      if (c * 32 >= S) break;
-      const float dist = ((s == S - 1) ? 1e10f : (zn[c] - zc[c])) * dnorm;
-      SampleTerms t = sample_terms(rw[c].w + nz[c], dist);
-      const float f = ok ? t.trans_factor : 1.0f;
-      const float incl = warp_scan_prod(f, lane);
-      float excl = __shfl_up_sync(CTX_FULL_MASK, incl, 1);
-      if (lane == 0) excl = 1.0f;
-      const float T = carry * excl;
-      const float w = ok ? t.alpha * T : 0.f;
-      carry *= __shfl_sync(CTX_FULL_MASK, incl, 31);
-      if (ok) {
-        weights[base + s] = w;
-        sr += w * sigmoidf_(rw[c].x);
-        sg += w * sigmoidf_(rw[c].y);
-        sb += w * sigmoidf_(rw[c].z);
-        sd += w * zc[c];
-        sa += w;
+      const float dist = ((s == S - 1) ? 1e10f : (zl[k + 1] - zl[k])) * dnorm;
+      const SampleTerms t = sample_terms(rw[k].w + nz[k], dist);
+      al[k] = ok ? t.alpha : 0.f;
+      pref[k] = run;
+      run *= ok ? t.trans_factor : 1.0f;
+    }
+    const float incl = warp_scan_prod(run, lane);
+    float excl = __shfl_up_sync(CTX_FULL_MASK, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    float w[K];
+    float sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      w[k] = al[k] * (excl * pref[k]);
+      if (s0 + k < S) {
+        sr += w[k] * sigmoidf_(rw[k].x);
+        sg += w[k] * sigmoidf_(rw[k].y);
+        sb += w[k] * sigmoidf_(rw[k].z);
+        sd += w[k] * zl[k];
+        sa += w[k];
       }
     }
+    store_row<K>(weights, base, s0, S, vec, w);
     sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sd = warp_sum(sd); sa = warp_sum(sa);
     if (lane == 0) {
       const float bg = white_bkgd ? (1.0f - sa) : 0.0f;
@@ -104,54 +154,66 @@ composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
 // Backward.  With t_k = 1-alpha_k+1e-10, T_i = prod_{k<i} t_k, w_i = alpha_i T_i and
 // G_i = dL/dw_i:   dL/dalpha_i = T_i * (G_i - S_i),
 //   S_i = sum_{j>i} G_j alpha_j prod_{i<k<j} t_k      (suffix affine scan; no division
-// by t_i, which is 1e-10 at an opaque sample -- SURVEY.md H5).
-template <int CH>
+// by t_i, which is 1e-10 at an opaque sample -- SURVEY.md H5).  S_i = U_{i+1} with
+// U_j = b_j + a_j U_{j+1}, a_j = t_j, b_j = G_j alpha_j: composed inside the lane, scanned across lanes, and
+// substituted back.
+template <int K>
 __global__ void __launch_bounds__(kCompWarps * 32)
 composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z,
                      const float* __restrict__ rays_d, const float* __restrict__ noise,
-                     int64_t R, int S, int white_bkgd,
+                     int64_t R, int S, int vec, int white_bkgd,
                      const float* __restrict__ g_rgb, const float* __restrict__ g_disp,
                      const float* __restrict__ g_acc, const float* __restrict__ g_weights,
                      const float* __restrict__ g_depth, float4* __restrict__ g_raw) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kCompWarps;
+  const int s0 = lane * K;
   for (int64_t ray = warp0; ray < R; ray += nwarps) {
     const float dx = rays_d[ray * 3 + 0], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
     const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
     const int64_t base = ray * S;
-    float4 rw[CH];
-    float zc[CH], gw[CH], alpha[CH], expo[CH], tf[CH], T[CH], dist[CH], sig[CH];
+    float4 rw[K];
+    float zl[K + 1], nz[K + 1], gw[K + 1];
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int s = c * 32 + lane;
-      const bool ok = s < S;
-      rw[c] = ok ? __ldg(raw + base + s) : make_float4(0.f, 0.f, 0.f, 0.f);
-      zc[c] = ok ? __ldg(z + base + s) : 0.f;
-      const float zn = (s + 1 < S) ? __ldg(z + base + s + 1) : 0.f;
-      const float nz = (noise != nullptr && ok) ? __ldg(noise + base + s) : 0.f;
-      gw[c] = (g_weights != nullptr && ok) ? __ldg(g_weights + base + s) : 0.f;
-      dist[c] = ((s == S - 1) ? 1e10f : (zn - zc[c])) * dnorm;
-      sig[c] = rw[c].w + nz;
+    for (int k = 0; k < K; ++k)
+      rw[k] = (s0 + k < S) ? __ldg(raw + base + s0 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+    load_row<K>(z, base, s0, S, vec, zl);
+    if (noise != nullptr) load_row<K>(noise, base, s0, S, vec, nz);
+    else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) nz[k] = 0.f;
     }
-    // forward recompute: T_i, alpha_i, and the ray totals needed by the disp gradient
-    float carry = 1.0f, sd = 0.f, sa = 0.f;
+    if (g_weights != nullptr) load_row<K>(g_weights, base, s0, S, vec, gw);
+    else {
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int s = c * 32 + lane;
+      for (int k = 0; k < K; ++k) gw[k] = 0.f;
+    }
+    zl[K] = __shfl_down_sync(CTX_FULL_MASK, zl[0], 1);
+    // forward recompute: expo (alpha, t follow from it), the in-lane transmittance prefix, the ray totals
+    float ex[K], dist[K], pref[K];
+    float run = 1.0f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int s = s0 + k;
       const bool ok = s < S;
-      SampleTerms t = sample_terms(sig[c], dist[c]);
-      alpha[c] = ok ? t.alpha : 0.f;
-      expo[c] = t.expo;
-      tf[c] = ok ? t.trans_factor : 1.0f;
-      const float incl = warp_scan_prod(tf[c], lane);
-      float excl = __shfl_up_sync(CTX_FULL_MASK, incl, 1);
-      if (lane == 0) excl = 1.0f;
-      T[c] = carry * excl;
-      carry *= __shfl_sync(CTX_FULL_MASK, incl, 31);
-      const float w = alpha[c] * T[c];
-      sd += w * zc[c];
-      sa += w;
+      dist[k] = ((s == S - 1) ? 1e10f : (zl[k + 1] - zl[k])) * dnorm;
+      const SampleTerms t = sample_terms(rw[k].w + nz[k], dist[k]);
+      ex[k] = ok ? t.expo : 1.0f;            // padded samples: alpha = 0, t = 1 + 1e-10 ~ identity (masked below)
+      pref[k] = run;
+      run *= ok ? t.trans_factor : 1.0f;
+    }
+    const float incl = warp_scan_prod(run, lane);
+    float excl = __shfl_up_sync(CTX_FULL_MASK, incl, 1);
+    if (lane == 0) excl = 1.0f;
+    float sd = 0.f, sa = 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (s0 + k < S) {
+        const float w = (1.0f - ex[k]) * (excl * pref[k]);
+        sd += w * zl[k];
+        sa += w;
+      }
     }
     sd = warp_sum(sd); sa = warp_sum(sa);
     const float gr = g_rgb ? g_rgb[ray * 3 + 0] : 0.f;
@@ -171,40 +233,64 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
       }
     }
     if (white_bkgd) ga -= (gr + gg + gb);
-    // reverse affine scan over chunks
-    float carry_u = 0.f;  // U of the first sample of the following chunk
+    // G_k, and the lane's composed map U_first = Bc + A * U_(first sample of the next lane)
+    float G[K];
+    float A = 1.0f, Bc = 0.f;
 #pragma unroll
-    for (int c = CH - 1; c >= 0; --c) {
-      const int s = c * 32 + lane;
-      const bool ok = s < S;
-      if (c * 32 >= S) continue;
-      const float cr = sigmoidf_(rw[c].x), cg = sigmoidf_(rw[c].y), cb = sigmoidf_(rw[c].z);
-      const float G = gw[c] + gr * cr + gg * cg + gb * cb + gd * zc[c] + ga;
-      float a = tf[c];                      // padded lanes: a = 1, b = 0 (identity map)
-      float b = ok ? G * alpha[c] : 0.f;
+    for (int k = K - 1; k >= 0; --k) {
+      const bool ok = s0 + k < S;
+      const float cr = sigmoidf_(rw[k].x), cg = sigmoidf_(rw[k].y), cb = sigmoidf_(rw[k].z);
+      G[k] = gw[k] + gr * cr + gg * cg + gb * cb + gd * zl[k] + ga;
+      const float alpha = 1.0f - ex[k];
+      const float a = ok ? ((1.0f - alpha) + 1e-10f) : 1.0f;
+      const float b = ok ? G[k] * alpha : 0.f;
+      Bc = b + a * Bc;
+      A = a * A;
+    }
+    {
+      float a = A, b = Bc;   // inclusive suffix scan over the lanes: (a, b) <- map of lanes [lane, 32)
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         const float a2 = __shfl_down_sync(CTX_FULL_MASK, a, o);
         const float b2 = __shfl_down_sync(CTX_FULL_MASK, b, o);
         if (lane + o < 32) { b = b + a * b2; a = a * a2; }
       }
-      const float U = b + a * carry_u;
-      float Snext = __shfl_down_sync(CTX_FULL_MASK, U, 1);
-      if (lane == 31) Snext = carry_u;
-      carry_u = __shfl_sync(CTX_FULL_MASK, U, 0);
+      Bc = b;                // = U of this lane's first sample (U past the end of the ray is 0)
+    }
+    float U = __shfl_down_sync(CTX_FULL_MASK, Bc, 1);
+    if (lane == 31) U = 0.f;
+#pragma unroll
+    for (int k = K - 1; k >= 0; --k) {
+      const bool ok = s0 + k < S;
+      const float alpha = 1.0f - ex[k];
+      const float T = excl * pref[k];
       if (ok) {
-        const float g_alpha = T[c] * (G - Snext);
-        const float g_sigma = (sig[c] > 0.f) ? g_alpha * expo[c] * dist[c] : 0.f;
-        const float w = alpha[c] * T[c];
+        const float cr = sigmoidf_(rw[k].x), cg = sigmoidf_(rw[k].y), cb = sigmoidf_(rw[k].z);
+        const float g_alpha = T * (G[k] - U);
+        const float sig = rw[k].w + nz[k];
+        const float g_sigma = (sig > 0.f) ? g_alpha * ex[k] * dist[k] : 0.f;
+        const float w = alpha * T;
         float4 o4;
         o4.x = w * gr * cr * (1.0f - cr);
         o4.y = w * gg * cg * (1.0f - cg);
         o4.z = w * gb * cb * (1.0f - cb);
         o4.w = g_sigma;
-        g_raw[base + s] = o4;
+        g_raw[base + s0 + k] = o4;
+        U = G[k] * alpha + ((1.0f - alpha) + 1e-10f) * U;
       }
     }
   }
+}
+
+// widest vector access (floats) that is aligned for every [R,S] row of the given pointers
+static inline int comp_vec(int S, std::initializer_list<const void*> ptrs) {
+  int vec = (S % 4 == 0) ? 4 : (S % 2 == 0 ? 2 : 1);
+  for (const void* p : ptrs) {
+    if (!p) continue;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    while (vec > 1 && (a % (vec * sizeof(float))) != 0) vec >>= 1;
+  }
+  return vec;
 }
 
 static inline int comp_grid(int64_t R) {
@@ -217,9 +303,11 @@ static inline int comp_grid(int64_t R) {
 
 }  // namespace ctx
 
+// K = samples per lane (S <= 32 K)
 #define CTX_COMP_DISPATCH(KERNEL, ...)                                                   \
   if (S <= 32) KERNEL<1><<<grid, block, 0, st>>>(__VA_ARGS__);                          \
   else if (S <= 64) KERNEL<2><<<grid, block, 0, st>>>(__VA_ARGS__);                     \
+  else if (S <= 96) KERNEL<3><<<grid, block, 0, st>>>(__VA_ARGS__);                     \
   else if (S <= 128) KERNEL<4><<<grid, block, 0, st>>>(__VA_ARGS__);                    \
   else if (S <= 192) KERNEL<6><<<grid, block, 0, st>>>(__VA_ARGS__);                    \
   else if (S <= 256) KERNEL<8><<<grid, block, 0, st>>>(__VA_ARGS__);                    \
@@ -236,7 +324,8 @@ extern "C" int ctx_composite_fwd(const float* raw, const float* z_vals, const fl
     return CTX_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ctx::comp_grid(R), block = ctx::kCompWarps * 32;
-  CTX_COMP_DISPATCH(ctx::composite_fwd_kernel, (const float4*)raw, z_vals, rays_d, noise, R, S,
+  const int vec = ctx::comp_vec(S, {z_vals, noise, weights});
+  CTX_COMP_DISPATCH(ctx::composite_fwd_kernel, (const float4*)raw, z_vals, rays_d, noise, R, S, vec,
                     white_bkgd, rgb_map, disp_map, acc_map, weights, depth_map)
   CTX_RETURN_LAST();
 }
@@ -251,7 +340,8 @@ extern "C" int ctx_composite_bwd(const float* raw, const float* z_vals, const fl
   if (!raw || !z_vals || !rays_d || !g_raw) return CTX_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ctx::comp_grid(R), block = ctx::kCompWarps * 32;
-  CTX_COMP_DISPATCH(ctx::composite_bwd_kernel, (const float4*)raw, z_vals, rays_d, noise, R, S,
+  const int vec = ctx::comp_vec(S, {z_vals, noise, g_weights});
+  CTX_COMP_DISPATCH(ctx::composite_bwd_kernel, (const float4*)raw, z_vals, rays_d, noise, R, S, vec,
                     white_bkgd, g_rgb, g_disp, g_acc, g_weights, g_depth, (float4*)g_raw)
   CTX_RETURN_LAST();
 }

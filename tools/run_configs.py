@@ -60,7 +60,9 @@ for lr in (12, 14, 16, 18, 20, 22):
         row["composite_fwd_gbs"] = R * (24 * S + 36) / t / 1e9
         N = 2 * S
         if N <= 1024:
-            t = timeit(lambda: ops.resample_raw(z[:, :S - 1].contiguous(), w[:, :S - 2].contiguous(), N, det=True), iters=3, warm=1)
+            bins_c, w_c = z[:, :S - 1].contiguous(), w[:, :S - 2].contiguous()   # (not part of the timed call)
+            with torch.no_grad():   # sample_pdf proper (no index output): 4(B + B-1) B read + 4N B written per ray
+                t = timeit(lambda: ops.resample(bins_c, w_c, N, det=True), iters=3, warm=1)
             row["resample_gbs"] = R * (4 * (S - 1) + 4 * (S - 2) + 4 * N) / t / 1e9
         pts = torch.rand(min(R * S, 1 << 25), 3, device=dev) * 4 - 2
         t = timeit(lambda: ops.posenc(pts, 10), iters=3, warm=1)
@@ -69,6 +71,7 @@ for lr in (12, 14, 16, 18, 20, 22):
             if k.endswith("_gbs"):
                 row[k.replace("_gbs", "_frac")] = row[k] * 1e9 / HBM
         sweep.append(row)
+        bins_c = w_c = None
         del raw, z, d, w, pts
         torch.cuda.empty_cache()
 out["cfg5_sweep"] = sweep
