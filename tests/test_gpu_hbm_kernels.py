@@ -287,6 +287,35 @@ def test_resample_merge_fused(cuda):
     assert torch.equal(z_all3.cpu(), torch.sort(torch.cat([z, s3], -1), -1)[0])
 
 
+def test_resample_merge_in_kernel_uniforms(cuda):
+    """det=False without explicit u: the kernel draws SORTED uniforms (order statistics through exponential spacings)
+    so that no sort is needed; check the contract instead of a stream: reproducible per seed, samples monotone and
+    inside the bins, z_all = sort(cat), and the samples follow the pdf (u recovered through the cdf is uniform)."""
+    from ctxnerf import ops
+    R, S, N = 2048, 64, 128
+    g = torch.Generator().manual_seed(4)
+    z = torch.sort(torch.rand(R, S, generator=g) * 4 + 2, -1)[0]
+    w = torch.rand(R, S, generator=g) ** 3
+    zs, z_all = ops.resample_merge(z.to(cuda), w.to(cuda), N, det=False, seed=11)
+    zs_b, z_all_b = ops.resample_merge(z.to(cuda), w.to(cuda), N, det=False, seed=11)
+    zs_c, _ = ops.resample_merge(z.to(cuda), w.to(cuda), N, det=False, seed=12)
+    assert torch.equal(zs, zs_b) and torch.equal(z_all, z_all_b) and not torch.equal(zs, zs_c)
+    zs, z_all = zs.cpu(), z_all.cpu()
+    assert (zs[:, 1:] >= zs[:, :-1]).all()
+    assert torch.equal(z_all, torch.sort(torch.cat([z, zs], -1), -1)[0])
+    bins = 0.5 * (z[:, 1:] + z[:, :-1])
+    assert (zs >= bins[:, :1]).all() and (zs <= bins[:, -1:]).all()
+    # push the samples back through the piecewise-linear cdf: the result must be uniform on [0, 1]
+    cdf = orc.pdf_to_cdf(w[:, 1:-1])
+    idx = torch.searchsorted(bins.contiguous(), zs.contiguous(), right=True).clamp(1, bins.shape[1] - 1)
+    b0, b1 = torch.gather(bins, 1, idx - 1), torch.gather(bins, 1, idx)
+    c0, c1 = torch.gather(cdf, 1, idx - 1), torch.gather(cdf, 1, idx)
+    u = c0 + (zs - b0) / (b1 - b0).clamp_min(1e-12) * (c1 - c0)
+    assert abs(u.mean().item() - 0.5) < 5e-3 and abs(u.var().item() - 1.0 / 12.0) < 3e-3
+    hist = torch.histc(u, bins=10, min=0.0, max=1.0) / u.numel()
+    assert (hist - 0.1).abs().max().item() < 6e-3, hist
+
+
 def test_sample_pdf_backward(cuda):
     from ctxnerf import ops
     g = torch.Generator().manual_seed(2)
