@@ -156,6 +156,57 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def run_cfg1(args):
+    """BASELINE configs[0] (the reference's own CPU-runnable case): the render-only chain on 4096 rays.  Not the
+    bench line of the metric; prints its own JSON line with the GPU chain and the CPU oracle timed side by side."""
+    from oracle import nerf_oracle as orc
+    from ctxnerf import ops, run_nerf_helpers as rh
+    dev = torch.device("cuda", 0)
+    R, S, Ni = 4096, 64, 128
+    raw, z, d = orc.cfg1_inputs(R, S)
+    raw_f = orc.cfg1_inputs(R, S + Ni, seed=1)[0]
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        ref = orc.cfg1_chain(raw, z, d, raw_f, Ni)
+    cpu_s = (time.perf_counter() - t0) / reps
+    rc, zc, dc, rfc = raw.to(dev), z.to(dev), d.to(dev), raw_f.to(dev)
+
+    def chain():
+        c = rh.raw2outputs(rc, zc, dc)
+        zs, z_all = ops.resample_merge(zc, c[3], Ni, det=True)
+        return c, zs, z_all, rh.raw2outputs(rfc, z_all, dc)
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            out = chain()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            out = chain()
+        b.record()
+        torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / args.steps
+    # parity stage by stage on the oracle's own intermediates (end to end the synthetic raw_fine is indexed by sample
+    # rank, so a one-ulp difference in a weight that reorders two depths would swap unrelated colours)
+    with torch.no_grad():
+        zs_g, zall_g = ops.resample_merge(zc, ref[0][3].to(dev), Ni, det=True)
+        fine_g = rh.raw2outputs(rfc, ref[2].to(dev), dc)
+    same_idx = bool(torch.equal(zall_g.cpu(), ref[2]) and torch.equal(zs_g.cpu(), ref[1]))
+
+    def rel(a, b):
+        return ((a.cpu() - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+    err = max(rel(out[0][0], ref[0][0]), rel(out[0][3], ref[0][3]), rel(fine_g[0], ref[3][0]), rel(fine_g[3], ref[3][3]),
+              rel(fine_g[4], ref[3][4]))
+    print(json.dumps({"metric": "rays/sec render-only chain (raw2outputs 64 -> sample_pdf det 128 -> merge -> raw2outputs 192)",
+                      "value": R / (ms * 1e-3), "unit": "rays/s", "n_gpus": 1, "steps": args.steps, "ms_per_step": ms,
+                      "config": {"workload": "configs[0]: 4096 rays x 64 coarse + 128 fine, synthetic raw"},
+                      "resample_bit_exact_on_oracle_weights": same_idx, "max_rel_err_composite": err,
+                      "cpu_baseline": {"value": R / cpu_s, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port",
+                                       "sample": f"the same chain x{reps}, oracle/nerf_oracle.py"}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -163,12 +214,19 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cfg1", action="store_true",
+                    help="BASELINE configs[0] instead of the training step: raw2outputs(64) -> sample_pdf(det, 128) -> "
+                         "merge -> raw2outputs(192) on 4096 rays, GPU chain beside the CPU oracle (parity-test sized)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank)
+        return
+    if args.cfg1:
+        if rank == 0:
+            run_cfg1(args)
         return
 
     import torch.distributed as dist

@@ -1,9 +1,25 @@
 """Stress the forward kernel for races: repeat launches, compare bitwise with the first result."""
 import os, sys, time
-sys.path[:0] = ["/root/repo", "/root/repo/contexture-nerf_b200", "/root/repo/tests"]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "contexture-nerf_b200")]
 import torch
-import test_gpu_mlp as T
 from ctxnerf import _lib
+from ctxnerf import run_nerf_helpers as rh
+
+
+def make_net(dev, views, seed, in_pts=63, out_ch=4):
+    torch.manual_seed(seed)
+    if views:
+        net = rh.NeRF(D=8, W=256, input_ch=in_pts, input_ch_views=27, skips=[4], use_viewdirs=True)
+    else:
+        net = rh.NeRF2D(D=8, W=256, input_ch=in_pts, output_ch=out_ch, skips=[4])
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.dim() == 1:
+                p.uniform_(-0.1, 0.1)
+    return net.to(dev)
+
+
 dev = torch.device("cuda:0")
 flags = int(os.environ.get("CTX_DBG", "0"))
 _lib.lib().ctx_mlp_set_debug(flags)
@@ -20,7 +36,7 @@ def report():
         print("   ", TAGS.get(e[0], e[0]), "block", e[1] >> 32, "warp", e[1] & 0xffffffff, "info", e[2], "parity", e[3])
 import atexit
 for (views, P, train) in ((False, 1000, False), (False, 4096, False), (True, 777, False), (True, 40000, False), (True, 20000, True)):
-    net, params = T._net(dev, views, seed=P, in_pts=63, out_ch=4)
+    net = make_net(dev, views, seed=P)
     g = torch.Generator().manual_seed(1)
     x = torch.randn(P, 90 if views else 63, generator=g).clamp(-1, 1).to(dev)
     bad = 0
