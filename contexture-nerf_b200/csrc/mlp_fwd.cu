@@ -9,17 +9,23 @@
 // between the tile pairs,
 //     MMA(l, A) | MMA(l, B) | MMA(l+1, A) | ...
 //                 epi(l, A) | epi(l, B)   | ...
-// so the TMEM->bias->ReLU->bf16->shared-memory epilogue of one pair (and, when
+// so the TMEM->ReLU->bf16->shared-memory epilogue of one pair (and, when
 // training, the activation-record stores) runs under the MMAs of the other one.
 // Weights are streamed twice per layer (once per pair) as 8 KB half-chunks by
 // 1-D bulk TMA through an 8-stage ring (1.2 MB of L2 reads per CTA per 256 points).
 //
 // Synchronisation: full/empty/acc_full barriers are local to each CTA (the MMA
-// completion is multicast to both with tcgen05.commit...multicast::cluster); the
-// leader's MMA thread additionally needs (a) the peer's weight half landed --
-// relayed by the peer's otherwise idle warp 1 with a remote mbarrier arrive -- and
-// (b) both CTAs' epilogue warps done with the next A operand (act_ready, 16 warp
-// arrivals, the peer's are remote).
+// completion is multicast to both with tcgen05.commit...multicast::cluster).  The
+// leader's `full` barrier of a ring pair counts two arrivals: its own producer's and
+// the peer's "my half landed too", relayed by the peer's otherwise idle warp 1 with a
+// remote mbarrier arrive -- so an issuer makes one wait per 16 KB of weights.  Each
+// issuer is ONE elected thread running the whole loop (no per-chunk elect / warp
+// sync); it also waits for both CTAs' epilogue warps to be done with the next A
+// operand (act_ready, 16 warp arrivals, the peer's are remote).  The two issuers
+// consume interleaved ring pairs and mbarrier waits only see the phase parity: the
+// first pairs of a layer phase check `empty` of the pair's previous use (possibly the
+// other issuer's) before trusting `full`.  tcgen05.wait::ld is tied to the loaded
+// registers so that their consumers cannot be scheduled above it.
 //
 // Reference semantics: NeRF2D.forward, /root/reference/src/run_nerf_helpers.py:106-135
 // (+ commented view branch :117-127); Embedder.embed :44-45.
