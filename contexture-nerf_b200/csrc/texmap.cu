@@ -1,0 +1,127 @@
+// texture_mapping + mask / background composite of the rasterised mesh.
+//
+// Reference call site: /root/reference/src/models/render.py:133-140 --
+//   image_features = kal.render.mesh.texture_mapping(uv_features, texture_map, mode)   (uv_features is detached, :121)
+//   image_features = image_features * mask ; image_features += 1 * (1 - mask)          (white background)
+// kaolin's texture_mapping (third party, un-vendored; restated in oracle/nerf_oracle.py) maps uv in [0,1] to
+// grid_sample coordinates (u*2-1, -(v*2-1)) and samples with align_corners=False, padding_mode='border'.
+// One thread per pixel: coordinates once, then per channel four gathers (bilinear) or one (nearest); the backward
+// scatters g_out * mask into the texture gradient with fp32 atomics (only the texture gets a gradient, as upstream).
+// HBM-bound: 8 B uv + 4 B mask read, 4C B written per pixel; the texture (12.6 MB at 1024^2 x 3) lives in L2.
+#include "ctx_common.cuh"
+
+namespace ctx {
+
+struct TexCoord {
+  int x0, y0, x1, y1;
+  float w00, w01, w10, w11;   // (y, x) corner weights
+};
+
+// grid_sample's unnormalise (align_corners=False) + border clip, in torch's operation order
+__device__ __forceinline__ float tex_unnormalize(float coord, int size) {
+  float x = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(coord, 1.0f), (float)size), 1.0f), 0.5f);
+  return fminf((float)(size - 1), fmaxf(x, 0.0f));
+}
+
+__device__ __forceinline__ TexCoord tex_coord(float u, float v, int H, int W, int bilinear) {
+  const float gx = __fsub_rn(__fmul_rn(u, 2.0f), 1.0f);
+  const float gy = -__fsub_rn(__fmul_rn(v, 2.0f), 1.0f);
+  const float ix = tex_unnormalize(gx, W), iy = tex_unnormalize(gy, H);
+  TexCoord t;
+  if (bilinear) {
+    const float fx = floorf(ix), fy = floorf(iy);
+    t.x0 = (int)fx; t.y0 = (int)fy; t.x1 = t.x0 + 1; t.y1 = t.y0 + 1;
+    const float ax = ix - fx, ay = iy - fy;        // distance to the north-west texel
+    t.w00 = (1.0f - ax) * (1.0f - ay); t.w01 = ax * (1.0f - ay);
+    t.w10 = (1.0f - ax) * ay;          t.w11 = ax * ay;
+    if (t.x1 > W - 1) { t.x1 = W - 1; t.w01 = 0.f; t.w11 = 0.f; }   // out-of-range corners contribute nothing
+    if (t.y1 > H - 1) { t.y1 = H - 1; t.w10 = 0.f; t.w11 = 0.f; }
+  } else {
+    t.x0 = t.x1 = (int)rintf(ix); t.y0 = t.y1 = (int)rintf(iy);     // nearbyint, as torch
+    t.w00 = 1.0f; t.w01 = t.w10 = t.w11 = 0.f;
+  }
+  return t;
+}
+
+__global__ void __launch_bounds__(256)
+texmap_fwd_kernel(const float2* __restrict__ uv, const float* __restrict__ tex, const float* __restrict__ mask,
+                  const float* __restrict__ bg, float* __restrict__ out, int64_t B, int64_t N, int tex_batch, int C,
+                  int H, int W, int bilinear) {
+  const int64_t total = B * N;
+  const int64_t plane = (int64_t)H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / N;
+    const float2 c = __ldg(uv + i);
+    const TexCoord t = tex_coord(c.x, c.y, H, W, bilinear);
+    const float m = mask ? __ldg(mask + i) : 1.0f;
+    const float* tb = tex + (tex_batch > 1 ? b : 0) * C * plane;
+    const int64_t o00 = (int64_t)t.y0 * W + t.x0, o01 = (int64_t)t.y0 * W + t.x1;
+    const int64_t o10 = (int64_t)t.y1 * W + t.x0, o11 = (int64_t)t.y1 * W + t.x1;
+    for (int ch = 0; ch < C; ++ch) {
+      const float* p = tb + ch * plane;
+      float v = t.w00 * __ldg(p + o00);
+      if (bilinear) v += t.w01 * __ldg(p + o01) + t.w10 * __ldg(p + o10) + t.w11 * __ldg(p + o11);
+      if (mask) v = v * m + (bg ? __ldg(bg + ch) : 0.f) * (1.0f - m);
+      out[i * C + ch] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+texmap_bwd_kernel(const float2* __restrict__ uv, const float* __restrict__ mask, const float* __restrict__ g_out,
+                  float* __restrict__ g_tex, int64_t B, int64_t N, int tex_batch, int C, int H, int W, int bilinear) {
+  const int64_t total = B * N;
+  const int64_t plane = (int64_t)H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float m = mask ? __ldg(mask + i) : 1.0f;
+    if (m == 0.f) continue;                          // background pixels carry no texture gradient
+    const int64_t b = i / N;
+    const float2 c = __ldg(uv + i);
+    const TexCoord t = tex_coord(c.x, c.y, H, W, bilinear);
+    float* tb = g_tex + (tex_batch > 1 ? b : 0) * C * plane;
+    const int64_t o00 = (int64_t)t.y0 * W + t.x0, o01 = (int64_t)t.y0 * W + t.x1;
+    const int64_t o10 = (int64_t)t.y1 * W + t.x0, o11 = (int64_t)t.y1 * W + t.x1;
+    for (int ch = 0; ch < C; ++ch) {
+      const float g = __ldg(g_out + i * C + ch) * m;
+      float* p = tb + ch * plane;
+      atomicAdd(p + o00, t.w00 * g);
+      if (bilinear) {
+        if (t.w01 != 0.f) atomicAdd(p + o01, t.w01 * g);
+        if (t.w10 != 0.f) atomicAdd(p + o10, t.w10 * g);
+        if (t.w11 != 0.f) atomicAdd(p + o11, t.w11 * g);
+      }
+    }
+  }
+}
+
+static inline int texmap_grid(int64_t total) {
+  int64_t blocks = ceil_div(total, 256);
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace ctx
+
+extern "C" int ctx_texmap_fwd(const float* uv, const float* tex, const float* mask, const float* bg, float* out,
+                              int64_t B, int64_t N, int tex_batch, int C, int H, int W, int mode, void* stream) {
+  if (B < 0 || N < 0 || C < 1 || H < 1 || W < 1 || (mode != 0 && mode != 1)) return CTX_ERR_BAD_ARG;
+  if (tex_batch != 1 && tex_batch != B) return CTX_ERR_BAD_ARG;
+  if (B * N == 0) return 0;
+  if (!uv || !tex || !out) return CTX_ERR_BAD_ARG;
+  ctx::texmap_fwd_kernel<<<ctx::texmap_grid(B * N), 256, 0, (cudaStream_t)stream>>>(
+      (const float2*)uv, tex, mask, bg, out, B, N, tex_batch, C, H, W, mode);
+  CTX_RETURN_LAST();
+}
+
+// g_tex is ACCUMULATED into (zero it first for a fresh gradient)
+extern "C" int ctx_texmap_bwd(const float* uv, const float* mask, const float* g_out, float* g_tex, int64_t B,
+                              int64_t N, int tex_batch, int C, int H, int W, int mode, void* stream) {
+  if (B < 0 || N < 0 || C < 1 || H < 1 || W < 1 || (mode != 0 && mode != 1)) return CTX_ERR_BAD_ARG;
+  if (tex_batch != 1 && tex_batch != B) return CTX_ERR_BAD_ARG;
+  if (B * N == 0) return 0;
+  if (!uv || !g_out || !g_tex) return CTX_ERR_BAD_ARG;
+  ctx::texmap_bwd_kernel<<<ctx::texmap_grid(B * N), 256, 0, (cudaStream_t)stream>>>(
+      (const float2*)uv, mask, g_out, g_tex, B, N, tex_batch, C, H, W, mode);
+  CTX_RETURN_LAST();
+}

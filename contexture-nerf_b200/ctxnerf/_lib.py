@@ -47,6 +47,8 @@ _SIGNATURES = {
     "ctx_mlp_bwd": (c_int, [P, P, P, P, P, P, c_int64, P, c_int, P]),
     "ctx_mlp_dgrad_ex": (c_int, [P, P, P, P, P, P, c_int64, c_int, P]),
     "ctx_mlp_wgrad_ex": (c_int, [P, P, P, c_int64, P, c_int, c_int, P]),
+    "ctx_texmap_fwd": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, P]),
+    "ctx_texmap_bwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, P]),
     "ctx_tanh01_fwd": (c_int, [P, P, c_int64, c_int, P]),
     "ctx_tanh01_bwd": (c_int, [P, P, P, P, c_int64, c_int, P]),
     "ctx_adam_step": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_int, c_float, c_float, P]),

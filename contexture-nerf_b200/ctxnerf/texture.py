@@ -60,3 +60,58 @@ def get_texture_map(texture_mlp, res: int):
     params = texture_mlp._param_list()
     need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
     return _TextureMapFn.apply(texture_mlp, int(res), need_grad, *params)
+
+
+class _TexMapFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, uv, texture, mask, bg, mode):
+        if not (uv.is_cuda and texture.is_cuda):
+            raise _lib.CtxNerfError("ctxnerf texture_mapping runs on CUDA tensors only (no CPU fallback)")
+        dev = uv.device
+        B = uv.shape[0]
+        dims = tuple(uv.shape[1:-1])
+        uv2 = uv.detach().reshape(B, -1, 2).float().contiguous()
+        N = uv2.shape[1]
+        tex = texture.float().contiguous()
+        Bt, C, H, W = tex.shape
+        if Bt != B and Bt != 1:
+            raise _lib.CtxNerfError("texture batch must be 1 or match uv")
+        m2 = mask.detach().reshape(B, N).float().contiguous() if mask is not None else None
+        bg2 = bg.detach().reshape(C).float().contiguous() if bg is not None else None
+        out = torch.empty(B, N, C, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            call("ctx_texmap_fwd", ptr(uv2), ptr(tex), ptr(m2), ptr(bg2), ptr(out), B, N, Bt, C, H, W, mode,
+                 stream_ptr(dev))
+        ctx.save_for_backward(uv2, m2 if m2 is not None else torch.empty(0, device=dev))
+        ctx.meta = (B, N, Bt, C, H, W, mode, m2 is not None)
+        return out.reshape(B, *dims, C)
+
+    @staticmethod
+    def backward(ctx, g):
+        uv2, m2 = ctx.saved_tensors
+        B, N, Bt, C, H, W, mode, has_mask = ctx.meta
+        dev = uv2.device
+        g2 = g.reshape(B, N, C).float().contiguous()
+        g_tex = torch.zeros(Bt, C, H, W, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            call("ctx_texmap_bwd", ptr(uv2), ptr(m2 if has_mask else None), ptr(g2), ptr(g_tex), B, N, Bt, C, H, W,
+                 mode, stream_ptr(dev))
+        return None, g_tex, None, None, None
+
+
+_MODES = {"nearest": 0, "bilinear": 1}
+
+
+def texture_mapping(texture_coordinates, texture_maps, mode="nearest", mask=None, background=None):
+    """``kal.render.mesh.texture_mapping(uv, texture, mode)`` as used at /root/reference/src/models/render.py:135
+    (uv [B,...,2] in [0,1], texture [B or 1, C, H, W] -> [B,...,C]); optionally fused with the two lines that follow
+    it there: ``* mask`` and ``+ background * (1 - mask)`` (``mask`` [B,...,1], ``background`` scalar or C values).
+    Only the texture receives a gradient (upstream detaches the coordinates).  'bicubic' is not provided."""
+    if mode not in _MODES:
+        raise _lib.CtxNerfError(f"texture_mapping mode {mode!r} not supported (nearest, bilinear)")
+    bg = None
+    if mask is not None and background is not None:
+        C = texture_maps.shape[1]
+        bg = torch.as_tensor(background, dtype=torch.float32, device=texture_maps.device).reshape(-1)
+        bg = bg.expand(C) if bg.numel() == 1 else bg
+    return _TexMapFn.apply(texture_coordinates, texture_maps, mask, bg, _MODES[mode])

@@ -159,6 +159,17 @@ int ctx_tanh01_fwd(const float* raw, float* out, int64_t P, int C, void* stream)
 int ctx_tanh01_bwd(const float* raw, const float* g_tex, const float* g_raw_in, float* g_raw, int64_t P, int C,
                    void* stream);
 
+/* ---- texture lookup of the rasterised mesh: kal.render.mesh.texture_mapping + mask / background composite,
+ * src/models/render.py:133-140.  uv [B,N,2] in [0,1] (v up), tex [tex_batch,C,H,W] with
+ * tex_batch == B or 1 (one atlas shared by every view: its gradient is the sum over the views), mode 0 = nearest,
+ * 1 = bilinear (grid_sample, align_corners=False, padding border).  mask (nullable, [B,N]): out = sample*mask +
+ * bg*(1-mask), bg (nullable) = C background values.  Only the texture receives a gradient (upstream detaches uv);
+ * ctx_texmap_bwd ACCUMULATES into g_tex.                                                                      */
+int ctx_texmap_fwd(const float* uv, const float* tex, const float* mask, const float* bg, float* out, int64_t B,
+                   int64_t N, int tex_batch, int C, int H, int W, int mode, void* stream);
+int ctx_texmap_bwd(const float* uv, const float* mask, const float* g_out, float* g_tex, int64_t B, int64_t N,
+                   int tex_batch, int C, int H, int W, int mode, void* stream);
+
 /* ---- training-step glue ------------------------------------------------------
  * img2mse(a,t) + img2mse(b,t) (src/run_nerf_helpers.py:9) and its gradient in one
  * pass: loss[0] = mean((a-t)^2) [+ mean((b-t)^2)], g_a = 2(a-t)/n*scale (b, g_*

@@ -397,6 +397,25 @@ def texture_map(params, res: int, multires: int = 10, bf16_operands: bool = Fals
     return tex.reshape(1, res, res, 3).permute(0, 3, 1, 2), out
 
 
+def texture_mapping(uv: torch.Tensor, texture: torch.Tensor, mode: str = "bilinear") -> torch.Tensor:
+    """kaolin.render.mesh.texture_mapping as called at /root/reference/src/models/render.py:135 (kaolin is third
+    party, un-vendored, no version pinned -> parity unpinned; this restates its documented behaviour): uv [B,...,2] in
+    [0,1] with v pointing up, texture [B,C,H,W]; uv -> grid_sample coordinates (2u-1, -(2v-1)),
+    align_corners=False, padding_mode='border'; returns [B,...,C]."""
+    B = uv.shape[0]
+    dims = uv.shape[1:-1]
+    g = uv.reshape(B, -1, 1, 2) * 2.0 - 1.0
+    g = torch.stack([g[..., 0], -g[..., 1]], -1)
+    out = torch.nn.functional.grid_sample(texture, g, mode=mode, align_corners=False, padding_mode="border")
+    return out.permute(0, 2, 3, 1).reshape(B, *dims, texture.shape[1])
+
+
+def render_composite(uv, texture, mask, background: float = 1.0, mode: str = "bilinear"):
+    """render.py:133-140: texture lookup, times the coverage mask, plus a constant background outside it."""
+    img = texture_mapping(uv, texture, mode) * mask
+    return img + background * (1 - mask)
+
+
 def img2mse(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     """reference :9"""
     return torch.mean((x - y) ** 2)

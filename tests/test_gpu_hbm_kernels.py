@@ -333,3 +333,51 @@ def test_sample_pdf_backward(cuda):
     sc = ops.resample(bins.to(cuda), wc, N, u=u.to(cuda))
     sc.backward(gs.to(cuda))
     torch.testing.assert_close(wc.grad.cpu(), w.grad, rtol=2e-3, atol=2e-4)
+
+
+# --------------------------------------------------------- texture mapping ---
+@pytest.mark.parametrize("mode", ["bilinear", "nearest"])
+@pytest.mark.parametrize("tex_batch", [1, 3])
+def test_texture_mapping_forward_backward(cuda, mode, tex_batch):
+    """kal.render.mesh.texture_mapping (+ mask / background lines of render.py:133-140) against the oracle's
+    grid_sample restatement; texture gradient against autograd (shared atlas: summed over the views)."""
+    from ctxnerf.texture import texture_mapping
+    g = torch.Generator().manual_seed(7)
+    B, Hh, Ww, C, res = 3, 37, 53, 3, 64
+    uv = torch.rand(B, Hh, Ww, 2, generator=g) * 1.1 - 0.05          # a few coordinates outside [0,1] (border clamp)
+    uv[0, 0, :4] = torch.tensor([[0.0, 0.0], [1.0, 1.0], [0.0, 1.0], [0.5 / res, 1 - 0.5 / res]])
+    tex = torch.rand(tex_batch, C, res, res + 8, generator=g)
+    mask = (torch.rand(B, Hh, Ww, 1, generator=g) > 0.3).float()
+    t_ref = tex.clone().requires_grad_(True)
+    ref = orc.render_composite(uv, t_ref.expand(B, -1, -1, -1), mask, 1.0, mode)
+    gout = torch.randn(ref.shape, generator=g)
+    (ref * gout).sum().backward()
+    t_gpu = tex.to(cuda).requires_grad_(True)
+    out = texture_mapping(uv.to(cuda), t_gpu, mode, mask=mask.to(cuda), background=1.0)
+    (out * gout.to(cuda)).sum().backward()
+    assert out.shape == ref.shape
+    if mode == "bilinear":
+        torch.testing.assert_close(out.detach().cpu(), ref.detach(), rtol=1e-5, atol=2e-6)
+        torch.testing.assert_close(t_gpu.grad.cpu(), t_ref.grad, rtol=1e-4, atol=1e-5)
+    else:   # nearest: a coordinate within an ulp of a texel boundary may pick the neighbour
+        same = (out.detach().cpu() - ref.detach()).abs().amax(-1) < 1e-6
+        assert same.float().mean().item() > 0.999
+    # plain call (no mask), the kaolin signature
+    plain = texture_mapping(uv.to(cuda), tex.to(cuda).expand(B, -1, -1, -1).contiguous(), mode)
+    ref_plain = orc.texture_mapping(uv, tex.expand(B, -1, -1, -1), mode)
+    if mode == "bilinear":
+        torch.testing.assert_close(plain.cpu(), ref_plain, rtol=1e-5, atol=2e-6)
+
+
+def test_texture_mapping_known_answers(cuda):
+    """uv at texel centres returns the texel (v points up: v = 1 is the first row)."""
+    from ctxnerf.texture import texture_mapping
+    res = 8
+    tex = torch.arange(res * res, dtype=torch.float32).reshape(1, 1, res, res)
+    xs = (torch.arange(res) + 0.5) / res
+    uv = torch.stack(torch.meshgrid(xs, xs, indexing="xy"), -1)[None]      # [1, res(v), res(u), 2]
+    for mode in ("nearest", "bilinear"):
+        out = texture_mapping(uv.to(cuda), tex.to(cuda), mode).cpu()[0, ..., 0]
+        assert torch.allclose(out, torch.flip(tex[0, 0], dims=[0]), atol=1e-5), mode
+    e = texture_mapping(torch.empty(1, 0, 2, device=cuda), tex.to(cuda), "bilinear")
+    assert e.shape == (1, 0, 1)

@@ -124,3 +124,20 @@ def test_texture_uv_grid_ordering():
     tex, raw = orc.texture_map(p, 8)
     assert tex.shape == (1, 3, 8, 8) and raw.shape == (64, 3)
     assert torch.allclose(tex[0, :, 2, 3], (torch.tanh(raw[2 * 8 + 3]) + 1) / 2)
+
+
+def test_texture_mapping_restatement():
+    """kaolin's texture_mapping as restated (render.py:135): v points up, texel centres reproduce the texels, uv outside
+    [0,1] clamps to the border, and the mask / background lines of render.py:137-140."""
+    res = 8
+    tex = torch.arange(res * res, dtype=torch.float32).reshape(1, 1, res, res)
+    xs = (torch.arange(res) + 0.5) / res
+    uv = torch.stack(torch.meshgrid(xs, xs, indexing="xy"), -1)[None]
+    for mode in ("nearest", "bilinear"):
+        out = orc.texture_mapping(uv, tex, mode)[0, ..., 0]
+        assert torch.allclose(out, torch.flip(tex[0, 0], dims=[0]), atol=1e-5)
+    corner = orc.texture_mapping(torch.tensor([[[-0.3, 1.7]]]), tex, "bilinear")
+    assert corner.item() == tex[0, 0, 0, 0].item()
+    mask = torch.tensor([[[1.0], [0.0]]])
+    img = orc.render_composite(torch.tensor([[[0.5, 0.5], [0.5, 0.5]]]), tex, mask, 1.0)
+    assert img[0, 1, 0].item() == 1.0 and img[0, 0, 0].item() != 1.0

@@ -44,3 +44,35 @@ out["res"] = res
 print(json.dumps(out))
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/texture_bench.json", "w"))
+
+# ---- texture_mapping + mask/background at the reference's render shape: 7 views x 1200 x 1200, 1024^2 x 3 atlas ----
+from ctxnerf.texture import texture_mapping
+B, Hh, Ww = 7, 1200, 1200
+uv = torch.rand(B, Hh, Ww, 2, device=dev)
+uv = (uv * 0.001 + torch.stack(torch.meshgrid(torch.linspace(0.05, 0.95, Hh, device=dev), torch.linspace(0.05, 0.95, Ww, device=dev),
+                                             indexing="ij"), -1)[None]).clamp(0, 1).contiguous()   # smooth uv, as a rasteriser gives
+mask = (torch.rand(B, Hh, Ww, 1, device=dev) > 0.4).float()
+atlas = torch.rand(1, 3, 1024, 1024, device=dev, requires_grad=True)
+gout = torch.randn(B, Hh, Ww, 3, device=dev)
+def tm_fwd():
+    with torch.no_grad():
+        texture_mapping(uv, atlas, "bilinear", mask=mask, background=1.0)
+def tm_fwdbwd():
+    atlas.grad = None
+    texture_mapping(uv, atlas, "bilinear", mask=mask, background=1.0).backward(gout)
+def lib_fwdbwd():   # the library route the reference takes (kaolin -> torch grid_sample), for scale
+    atlas.grad = None
+    g = uv.reshape(B, -1, 1, 2) * 2 - 1
+    g = torch.stack([g[..., 0], -g[..., 1]], -1)
+    img = torch.nn.functional.grid_sample(atlas.expand(B, -1, -1, -1), g, mode="bilinear", align_corners=False, padding_mode="border")
+    img = img.permute(0, 2, 3, 1).reshape(B, Hh, Ww, 3)
+    img = img * mask + 1.0 * (1 - mask)
+    img.backward(gout)
+npx = B * Hh * Ww
+t = timeit(tm_fwd); out["texmap_fwd_ms_v_along_x"] = t; out["texmap_fwd_gbs_v_along_x"] = npx * (8 + 4 + 12) / t / 1e6
+uv = torch.flip(uv, dims=[-1]).contiguous()     # u along the image x axis: neighbouring pixels read neighbouring texels
+t = timeit(tm_fwd); out["texmap_fwd_ms"] = t; out["texmap_fwd_gbs"] = npx * (8 + 4 + 12) / t / 1e6
+t = timeit(tm_fwdbwd); out["texmap_fwdbwd_ms"] = t
+out["torch_grid_sample_fwdbwd_ms"] = timeit(lib_fwdbwd)
+print(json.dumps(out))
+json.dump(out, open("gpurun_out/texture_bench.json", "w"))
