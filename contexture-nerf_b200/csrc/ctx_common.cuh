@@ -73,4 +73,17 @@ __device__ __forceinline__ float philox_uniform(uint64_t seed, uint64_t stream, 
   return u01(sel == 0 ? r.x : sel == 1 ? r.y : sel == 2 ? r.z : r.w);
 }
 
+// cudaFuncSetAttribute is per device: remember which devices a launcher has already prepared (one process may drive
+// several GPUs even though the training path uses one process per GPU)
+struct DeviceOnce {
+  bool done[64] = {};
+  bool needed() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 }  // namespace ctx

@@ -332,12 +332,11 @@ int ctx_launch_dgrad(const CtxMlpNet& net, const void* wtpacked, const float* fp
   int n = 0;
   for (int l = net.n_layers - 1; l >= 1; --l) { a.step_src[n] = l; a.step_dst[n] = l - 1; ++n; }
   a.n_steps = n;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static ctx::DeviceOnce attr_once;
+  if (attr_once.needed()) {
     cudaError_t e = cudaFuncSetAttribute(ctx::mlp_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)ctx::kDgSmemBytes);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
   const int64_t citers = ctx::ceil_div(P, (int64_t)ctx::kTileM * 4);
   int cap = ctx::kNumSMs / 2;   // one cluster per SM pair; a smaller SM budget leaves room for a concurrent kernel

@@ -548,13 +548,12 @@ extern "C" int ctx_mlp_fwd(const void* net_host, const void* wpacked, const floa
   using KernelFn = void (*)(ctx::MlpFwdArgs);
   static const KernelFn kernels[4] = {ctx::mlp_fwd_kernel<false, false>, ctx::mlp_fwd_kernel<false, true>,
                                       ctx::mlp_fwd_kernel<true, false>, ctx::mlp_fwd_kernel<true, true>};
-  static bool attr_set = false;
-  if (!attr_set) {
+  static ctx::DeviceOnce attr_once;
+  if (attr_once.needed()) {
     for (KernelFn k : kernels) {
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx::kMlp2SmemBytes);
       if (e != cudaSuccess) return (int)e;
     }
-    attr_set = true;
   }
   cudaError_t e = cudaMemsetAsync(out, 0, (size_t)P * a.net.out_ch * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;

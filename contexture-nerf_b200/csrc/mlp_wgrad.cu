@@ -243,12 +243,11 @@ extern "C" int ctx_mlp_wgrad_ex(const void* net_host, const void* acts, const vo
   const int D = views ? net.n_layers - 2 : net.n_layers;
   if (n_grads != 2 * D + (views ? 8 : 2)) return CTX_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static ctx::DeviceOnce attr_once;
+  if (attr_once.needed()) {
     cudaError_t e = cudaFuncSetAttribute(ctx::mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)ctx::kWgSmemBytes);
     if (e != cudaSuccess) return (int)e;
-    attr_set = true;
   }
   // ---------------- wgrad ----------------
   {
