@@ -291,3 +291,76 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
         ret['acc0'] = acc_map_0
         ret['z_std'] = torch.std(z_samples, dim=-1, unbiased=False)
     return ret
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Upstream outer driver: nerf-pytorch's run_nerf.py render / batchify_rays / render_path, the
+# callers of render_rays that the reference's pointer comment (src/run_nerf_helpers.py:131-133) refers to.  The
+# module is third party and un-vendored, so these follow its published call contract (argument names, defaults,
+# return order); nothing here has a counterpart to check against inside /root/reference.
+def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
+    """render_rays over ``chunk``-sized slices of a [N, 8|11] ray batch; dict of concatenated outputs."""
+    parts = {}
+    for i in range(0, rays_flat.shape[0], chunk):
+        ret = render_rays(rays_flat[i:i + chunk], **kwargs)
+        for k, v in ret.items():
+            parts.setdefault(k, []).append(v)
+    return {k: torch.cat(v, 0) for k, v in parts.items()}
+
+
+def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
+           c2w_staticcam=None, **kwargs):
+    """Render a full image (``c2w`` given) or an explicit ray batch (``rays`` = (rays_o, rays_d)).
+    Returns ``[rgb_map, disp_map, acc_map, extras]`` with the maps shaped like the input rays."""
+    if c2w is not None:
+        rays_o, rays_d = get_rays(H, W, K, c2w)
+    else:
+        rays_o, rays_d = rays
+    rays_o, rays_d = _to_cuda(rays_o), _to_cuda(rays_d)
+    viewdirs = None
+    if use_viewdirs:
+        viewdirs = rays_d
+        if c2w_staticcam is not None:   # view directions of `c2w`, geometry of the static camera
+            rays_o, rays_d = get_rays(H, W, K, c2w_staticcam)
+        viewdirs = viewdirs / torch.norm(viewdirs, dim=-1, keepdim=True)
+        viewdirs = viewdirs.reshape(-1, 3).float()
+    sh = rays_d.shape
+    if ndc:
+        rays_o, rays_d = ndc_rays(H, W, K[0][0], 1., rays_o, rays_d)
+    rays_o = rays_o.reshape(-1, 3).float()
+    rays_d = rays_d.reshape(-1, 3).float()
+    near_t = near * torch.ones_like(rays_d[..., :1])
+    far_t = far * torch.ones_like(rays_d[..., :1])
+    rays_cat = torch.cat([rays_o, rays_d, near_t, far_t], -1)
+    if use_viewdirs:
+        rays_cat = torch.cat([rays_cat, viewdirs], -1)
+    all_ret = batchify_rays(rays_cat, chunk, **kwargs)
+    for k in all_ret:
+        all_ret[k] = all_ret[k].reshape(list(sh[:-1]) + list(all_ret[k].shape[1:]))
+    k_extract = ['rgb_map', 'disp_map', 'acc_map']
+    ret_list = [all_ret[k] for k in k_extract]
+    ret_dict = {k: all_ret[k] for k in all_ret if k not in k_extract}
+    return ret_list + [ret_dict]
+
+
+def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0):
+    """Render one image per pose; returns (rgbs, disps) as stacked numpy arrays.  (Writing PNGs needs imageio,
+    which this image does not have: ``savedir`` is accepted and ignored unless imageio imports.)"""
+    H, W, focal = hwf
+    if render_factor != 0:
+        H, W, focal = H // render_factor, W // render_factor, focal / render_factor
+        K = [[K[0][0] / render_factor, 0., K[0][2] / render_factor],
+             [0., K[1][1] / render_factor, K[1][2] / render_factor], [0., 0., 1.]]
+    rgbs, disps = [], []
+    for i, c2w in enumerate(render_poses):
+        with torch.no_grad():
+            rgb, disp, acc, _ = render(H, W, K, chunk=chunk, c2w=torch.as_tensor(c2w)[:3, :4], **render_kwargs)
+        rgbs.append(rgb.cpu().numpy())
+        disps.append(disp.cpu().numpy())
+        if savedir is not None:
+            try:
+                import imageio
+                imageio.imwrite(f"{savedir}/{i:03d}.png", to8b(rgbs[-1]))
+            except ImportError:
+                pass
+    return np.stack(rgbs, 0), np.stack(disps, 0)

@@ -283,3 +283,31 @@ def test_backward_with_sm_budget(cuda, max_sms):
     from ctxnerf._lib import CtxNerfError
     with pytest.raises(CtxNerfError):
         mlp_wgrad(net, acts, d0, P, max_sms=2)
+
+
+def test_upstream_render_driver(cuda):
+    """render / batchify_rays / render_path (upstream run_nerf.py contract) are thin drivers over render_rays: a full
+    image rendered in chunks equals one render_rays call on the same rays."""
+    from ctxnerf import run_nerf_helpers as rh
+    from ctxnerf.workloads import orbit_camera
+    coarse, _ = _net(cuda, True, seed=41)
+    fine, _ = _net(cuda, True, seed=42)
+    H = W = 24
+    K, c2w = orbit_camera(H, W, focal=30.0)
+    kw = dict(network_fn=coarse, network_query_fn=rh.FusedQuery(), N_samples=64, N_importance=128, network_fine=fine,
+              perturb=0.0, white_bkgd=True)
+    with torch.no_grad():
+        rgb, disp, acc, extras = rh.render(H, W, K, chunk=200, c2w=c2w, ndc=False, near=2.0, far=6.0, use_viewdirs=True,
+                                           **kw)
+        ro, rd = rh.get_rays(H, W, K, c2w)
+        vd = rd / rd.norm(dim=-1, keepdim=True)
+        rays = torch.cat([ro.reshape(-1, 3), rd.reshape(-1, 3), torch.full((H * W, 1), 2.0, device=rd.device),
+                          torch.full((H * W, 1), 6.0, device=rd.device), vd.reshape(-1, 3)], -1)
+        one = rh.render_rays(rays, **kw)
+        rgbs, disps = rh.render_path([torch.cat([torch.as_tensor(c2w, dtype=torch.float32), torch.tensor([[0., 0., 0., 1.]])])],
+                                     (H, W, 30.0), K, 300, dict(kw, ndc=False, near=2.0, far=6.0, use_viewdirs=True))
+    assert rgb.shape == (H, W, 3) and disp.shape == (H, W) and set(extras) >= {"rgb0", "disp0", "acc0", "z_std"}
+    torch.testing.assert_close(rgb.reshape(-1, 3), one["rgb_map"], rtol=0, atol=1e-6)
+    torch.testing.assert_close(extras["rgb0"].reshape(-1, 3), one["rgb0"], rtol=0, atol=1e-6)
+    assert rgbs.shape == (1, H, W, 3) and disps.shape == (1, H, W)
+    assert np.allclose(rgbs[0], rgb.cpu().numpy(), atol=1e-6)
