@@ -9,6 +9,7 @@
 // scatters g_out * mask into the texture gradient with fp32 atomics (only the texture gets a gradient, as upstream).
 // HBM-bound: 8 B uv + 4 B mask read, 4C B written per pixel; the texture (12.6 MB at 1024^2 x 3) lives in L2.
 #include "ctx_common.cuh"
+#include <initializer_list>
 
 namespace ctx {
 
@@ -94,6 +95,70 @@ texmap_bwd_kernel(const float2* __restrict__ uv, const float* __restrict__ mask,
   }
 }
 
+// C == 3, N % 4 == 0, 16-byte aligned rows: four consecutive pixels per thread -- uv as two float4, mask as one,
+// the twelve outputs as three float4 stores (48 contiguous bytes), 48 independent gathers in flight per thread;
+// blockIdx.y is the view, so no 64-bit division.
+template <bool kBwd>
+__global__ void __launch_bounds__(256)
+texmap_rgb4_kernel(const float4* __restrict__ uv, const float* __restrict__ tex, const float4* __restrict__ mask,
+                   const float* __restrict__ bg, float4* __restrict__ io, float* __restrict__ g_tex, int64_t N,
+                   int tex_batch, int H, int W, int bilinear) {
+  const int64_t b = blockIdx.y;
+  const int64_t plane = (int64_t)H * W;
+  const int64_t nq = N >> 2;
+  const int64_t tex_off = (tex_batch > 1 ? b : 0) * 3 * plane;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i4 = b * nq + q;                   // index of this group of four pixels
+    const float4 c01 = __ldg(uv + 2 * i4), c23 = __ldg(uv + 2 * i4 + 1);
+    const float4 m4 = mask ? __ldg(mask + i4) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float us[4] = {c01.x, c01.z, c23.x, c23.z}, vs[4] = {c01.y, c01.w, c23.y, c23.w};
+    const float ms[4] = {m4.x, m4.y, m4.z, m4.w};
+    float v[12];
+    if (kBwd) {
+      const float4 a = __ldg(io + 3 * i4), bq = __ldg(io + 3 * i4 + 1), cq = __ldg(io + 3 * i4 + 2);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = bq.x; v[5] = bq.y; v[6] = bq.z; v[7] = bq.w;
+      v[8] = cq.x; v[9] = cq.y; v[10] = cq.z; v[11] = cq.w;
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const TexCoord t = tex_coord(us[p], vs[p], H, W, bilinear);
+      const int64_t o00 = (int64_t)t.y0 * W + t.x0, o01 = (int64_t)t.y0 * W + t.x1;
+      const int64_t o10 = (int64_t)t.y1 * W + t.x0, o11 = (int64_t)t.y1 * W + t.x1;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        if (!kBwd) {
+          const float* pl = tex + tex_off + ch * plane;
+          float r = t.w00 * __ldg(pl + o00);
+          if (bilinear) r += t.w01 * __ldg(pl + o01) + t.w10 * __ldg(pl + o10) + t.w11 * __ldg(pl + o11);
+          if (mask) r = r * ms[p] + (bg ? __ldg(bg + ch) : 0.f) * (1.0f - ms[p]);
+          v[p * 3 + ch] = r;
+        } else if (ms[p] != 0.f) {
+          float* pl = g_tex + tex_off + ch * plane;
+          const float g = v[p * 3 + ch] * ms[p];
+          atomicAdd(pl + o00, t.w00 * g);
+          if (bilinear) {
+            if (t.w01 != 0.f) atomicAdd(pl + o01, t.w01 * g);
+            if (t.w10 != 0.f) atomicAdd(pl + o10, t.w10 * g);
+            if (t.w11 != 0.f) atomicAdd(pl + o11, t.w11 * g);
+          }
+        }
+      }
+    }
+    if (!kBwd) {
+      io[3 * i4] = make_float4(v[0], v[1], v[2], v[3]);
+      io[3 * i4 + 1] = make_float4(v[4], v[5], v[6], v[7]);
+      io[3 * i4 + 2] = make_float4(v[8], v[9], v[10], v[11]);
+    }
+  }
+}
+
+static inline bool texmap_vec_ok(int64_t N, int C, std::initializer_list<const void*> ptrs) {
+  if (C != 3 || (N & 3) != 0) return false;
+  for (const void* p : ptrs)
+    if (p && (reinterpret_cast<uintptr_t>(p) & 15) != 0) return false;
+  return true;
+}
+
 static inline int texmap_grid(int64_t total) {
   int64_t blocks = ceil_div(total, 256);
   const int64_t cap = (int64_t)kNumSMs * 8;
@@ -109,6 +174,12 @@ extern "C" int ctx_texmap_fwd(const float* uv, const float* tex, const float* ma
   if (tex_batch != 1 && tex_batch != B) return CTX_ERR_BAD_ARG;
   if (B * N == 0) return 0;
   if (!uv || !tex || !out) return CTX_ERR_BAD_ARG;
+  if (B <= 65535 && ctx::texmap_vec_ok(N, C, {uv, mask, out})) {
+    dim3 grid((unsigned)ctx::texmap_grid(N / 4), (unsigned)B);
+    ctx::texmap_rgb4_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)uv, tex, (const float4*)mask, bg, (float4*)out, nullptr, N, tex_batch, H, W, mode);
+    CTX_RETURN_LAST();
+  }
   ctx::texmap_fwd_kernel<<<ctx::texmap_grid(B * N), 256, 0, (cudaStream_t)stream>>>(
       (const float2*)uv, tex, mask, bg, out, B, N, tex_batch, C, H, W, mode);
   CTX_RETURN_LAST();
@@ -121,6 +192,13 @@ extern "C" int ctx_texmap_bwd(const float* uv, const float* mask, const float* g
   if (tex_batch != 1 && tex_batch != B) return CTX_ERR_BAD_ARG;
   if (B * N == 0) return 0;
   if (!uv || !g_out || !g_tex) return CTX_ERR_BAD_ARG;
+  if (B <= 65535 && ctx::texmap_vec_ok(N, C, {uv, mask, g_out})) {
+    dim3 grid((unsigned)ctx::texmap_grid(N / 4), (unsigned)B);
+    ctx::texmap_rgb4_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)uv, nullptr, (const float4*)mask, nullptr, (float4*)const_cast<float*>(g_out), g_tex, N,
+        tex_batch, H, W, mode);
+    CTX_RETURN_LAST();
+  }
   ctx::texmap_bwd_kernel<<<ctx::texmap_grid(B * N), 256, 0, (cudaStream_t)stream>>>(
       (const float2*)uv, mask, g_out, g_tex, B, N, tex_batch, C, H, W, mode);
   CTX_RETURN_LAST();

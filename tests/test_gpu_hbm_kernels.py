@@ -338,12 +338,13 @@ def test_sample_pdf_backward(cuda):
 # --------------------------------------------------------- texture mapping ---
 @pytest.mark.parametrize("mode", ["bilinear", "nearest"])
 @pytest.mark.parametrize("tex_batch", [1, 3])
-def test_texture_mapping_forward_backward(cuda, mode, tex_batch):
+@pytest.mark.parametrize("Hh,Ww", [(37, 53), (36, 52)])      # scalar path / four-pixels-per-thread path
+def test_texture_mapping_forward_backward(cuda, mode, tex_batch, Hh, Ww):
     """kal.render.mesh.texture_mapping (+ mask / background lines of render.py:133-140) against the oracle's
     grid_sample restatement; texture gradient against autograd (shared atlas: summed over the views)."""
     from ctxnerf.texture import texture_mapping
     g = torch.Generator().manual_seed(7)
-    B, Hh, Ww, C, res = 3, 37, 53, 3, 64
+    B, C, res = 3, 3, 64
     uv = torch.rand(B, Hh, Ww, 2, generator=g) * 1.1 - 0.05          # a few coordinates outside [0,1] (border clamp)
     uv[0, 0, :4] = torch.tensor([[0.0, 0.0], [1.0, 1.0], [0.0, 1.0], [0.5 / res, 1 - 0.5 / res]])
     tex = torch.rand(tex_batch, C, res, res + 8, generator=g)
