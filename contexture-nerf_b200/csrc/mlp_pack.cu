@@ -112,8 +112,9 @@ __global__ void mlp_pack_kernel(const __grid_constant__ PackArgs a) {
 extern "C" int ctx_mlp_net_bytes(void) { return (int)sizeof(CtxMlpNet); }
 
 extern "C" int ctx_mlp_describe(int D, uint32_t skip_mask, int in_pts, int in_views, int out_ch, void* net_out) {
-  if (!net_out || D < 1 || D > 16 || in_pts < 1 || in_pts > CTX_MLP_XP_PAD || in_views < 0 ||
-      in_views > CTX_MLP_XD_PAD || out_ch < 1 || out_ch > 4)
+  // (the last channel of each padded encoding is the constant 1 that carries the bias through the GEMM)
+  if (!net_out || D < 2 || D > 16 || in_pts < 1 || in_pts > CTX_MLP_XP_PAD - 1 || in_views < 0 ||
+      in_views > CTX_MLP_XD_PAD - 1 || out_ch < 1 || out_ch > 4)
     return CTX_ERR_BAD_ARG;
   if (in_views > 0 && out_ch != 4) return CTX_ERR_BAD_ARG;
   CtxMlpNet net;

@@ -311,3 +311,43 @@ def test_upstream_render_driver(cuda):
     torch.testing.assert_close(extras["rgb0"].reshape(-1, 3), one["rgb0"], rtol=0, atol=1e-6)
     assert rgbs.shape == (1, H, W, 3) and disps.shape == (1, H, W)
     assert np.allclose(rgbs[0], rgb.cpu().numpy(), atol=1e-6)
+
+
+@pytest.mark.parametrize("D,skips,in_pts,out_ch", [(2, [], 63, 4), (4, [1], 42, 3), (8, [2, 5], 21, 1), (6, [4], 63, 2),
+                                                    (8, [0], 63, 4)])
+def test_mlp_other_depths_and_skips(cuda, D, skips, in_pts, out_ch):
+    """The kernels are generic in depth, skip positions, input width (<= 63) and output width (<= 4): forward and
+    backward parity for shapes other than the reference's D=8 / skips=[4]."""
+    from ctxnerf import run_nerf_helpers as rh
+    torch.manual_seed(100 + D)
+    net = rh.NeRF2D(D=D, W=256, input_ch=in_pts, output_ch=out_ch, skips=skips)
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.dim() == 1:
+                p.uniform_(-0.1, 0.1)
+    params = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net = net.to(cuda)
+    P = 2500
+    g = torch.Generator().manual_seed(D)
+    x = torch.randn(P, in_pts, generator=g).clamp(-1, 1)
+    out = net(x.to(cuda))
+    ref32 = orc.mlp_forward(params, x, D=D, skips=tuple(skips))
+    pr = {k: t.clone().requires_grad_(True) for k, t in params.items()}
+    ref16 = orc.mlp_forward_bf16(pr, x, D=D, skips=tuple(skips))
+    _check(out.detach(), ref32, ref16.detach(), f"mlp D={D} skips={skips} in={in_pts} out={out_ch}")
+    (out.pow(2).mean() + out.mean()).backward()
+    (ref16.pow(2).mean() + ref16.mean()).backward()
+    for name, p in net.named_parameters():
+        ref = pr[name].grad
+        l2 = ((p.grad.cpu() - ref).norm() / (ref.norm() + 1e-12)).item()
+        assert l2 < 2e-2, (name, l2)
+
+
+def test_mlp_rejects_unsupported_shapes(cuda):
+    from ctxnerf import run_nerf_helpers as rh
+    from ctxnerf._lib import CtxNerfError
+    x = torch.rand(10, 64, device=cuda)
+    with pytest.raises(CtxNerfError):
+        rh.NeRF2D(D=8, W=256, input_ch=64, output_ch=4, skips=[4]).to(cuda)(x)      # no room for the bias channel
+    with pytest.raises(CtxNerfError):
+        rh.NeRF2D(D=8, W=128, input_ch=63, output_ch=4, skips=[4]).to(cuda)(x[:, :63])   # width is fixed at 256
