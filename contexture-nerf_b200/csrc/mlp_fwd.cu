@@ -523,8 +523,9 @@ extern "C" int ctx_mlp_fwd(const void* net_host, const void* wpacked, const floa
                             const float* x, int x_ld, const float* rays_o, const float* rays_d,
                             const float* viewdirs, const float* z, int S, int L_pts, int L_dirs, int64_t P,
                             float* out, void* acts, void* stream) {
-  if (!net_host || !wpacked || !fparams || !out || P < 0) return CTX_ERR_BAD_ARG;
-  if (P == 0) return 0;
+  if (P < 0) return CTX_ERR_BAD_ARG;
+  if (P == 0) return 0;                       // empty batch: nothing to launch (its pointers may be null)
+  if (!net_host || !wpacked || !fparams || !out) return CTX_ERR_BAD_ARG;
   ctx::MlpFwdArgs a;
   a.net = *reinterpret_cast<const CtxMlpNet*>(net_host);
   if (mode == 0) {

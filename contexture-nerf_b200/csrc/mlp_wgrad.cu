@@ -236,8 +236,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const __grid_c
 // pack into whole SM pairs and a concurrent cluster kernel (dgrad of the other network) finds free pairs.
 extern "C" int ctx_mlp_wgrad_ex(const void* net_host, const void* acts, const void* dacts, int64_t P,
                                 float* const* grads, int n_grads, int max_sms, void* stream) {
-  if (!net_host || !acts || !dacts || !grads || P < 0) return CTX_ERR_BAD_ARG;
+  if (P < 0) return CTX_ERR_BAD_ARG;
   if (P == 0) return 0;
+  if (!net_host || !acts || !dacts || !grads) return CTX_ERR_BAD_ARG;
   const CtxMlpNet& net = *reinterpret_cast<const CtxMlpNet*>(net_host);
   const bool views = net.in_views > 0;
   const int D = views ? net.n_layers - 2 : net.n_layers;
@@ -349,8 +350,9 @@ extern "C" int ctx_mlp_wgrad(const void* net_host, const void* acts, const void*
 
 extern "C" int ctx_mlp_dgrad_ex(const void* net_host, const void* wtpacked, const float* fparams, const float* g_out,
                                 const void* acts, void* dacts, int64_t P, int max_sms, void* stream) {
-  if (!net_host || !wtpacked || !fparams || !g_out || !acts || !dacts || P < 0) return CTX_ERR_BAD_ARG;
+  if (P < 0) return CTX_ERR_BAD_ARG;
   if (P == 0) return 0;
+  if (!net_host || !wtpacked || !fparams || !g_out || !acts || !dacts) return CTX_ERR_BAD_ARG;
   return ctx_launch_dgrad(*reinterpret_cast<const CtxMlpNet*>(net_host), wtpacked, fparams, g_out, acts, dacts, P,
                           max_sms, (cudaStream_t)stream);
 }

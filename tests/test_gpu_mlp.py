@@ -351,3 +351,20 @@ def test_mlp_rejects_unsupported_shapes(cuda):
         rh.NeRF2D(D=8, W=256, input_ch=64, output_ch=4, skips=[4]).to(cuda)(x)      # no room for the bias channel
     with pytest.raises(CtxNerfError):
         rh.NeRF2D(D=8, W=128, input_ch=63, output_ch=4, skips=[4]).to(cuda)(x[:, :63])   # width is fixed at 256
+
+
+@pytest.mark.parametrize("P", [0, 1, 129, 513])
+def test_mlp_ragged_and_empty_batches(cuda, P):
+    """Tile-ragged point counts (1, one past a tile, one past a 4-tile cluster iteration) and the empty batch."""
+    net, params = _net(cuda, True, seed=5)
+    g = torch.Generator().manual_seed(P)
+    x = torch.randn(P, 90, generator=g).clamp(-1, 1)
+    out = net(x.to(cuda))
+    assert out.shape == (P, 4)
+    if P == 0:
+        out.sum().backward()          # nothing to do, but must not fail
+        return
+    ref16 = orc.mlp_forward_bf16(params, x, input_ch_views=27)
+    assert (out.detach().cpu() - ref16).abs().max().item() < 1e-2 * max(ref16.abs().max().item(), 1.0)
+    out.square().sum().backward()
+    assert all(torch.isfinite(p.grad).all() for p in net.parameters())
