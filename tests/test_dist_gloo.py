@@ -108,3 +108,10 @@ def test_product_fails_loudly_without_cuda():
     from ctxnerf import run_nerf_helpers as rh
     with pytest.raises(_lib.CtxNerfError):
         rh.sample_pdf(torch.zeros(2, 5), torch.zeros(2, 4), 8, det=True)
+    from ctxnerf.texture import texture_mapping
+    with pytest.raises(_lib.CtxNerfError):
+        texture_mapping(torch.zeros(1, 4, 2), torch.zeros(1, 3, 8, 8), "bilinear")
+    with pytest.raises(_lib.CtxNerfError):
+        texture_mapping(torch.zeros(1, 4, 2), torch.zeros(1, 3, 8, 8), "bicubic")
+    with pytest.raises((_lib.CtxNerfError, RuntimeError)):
+        rh.NeRF2D(D=8, W=256, input_ch=42, output_ch=3, skips=[4])(torch.zeros(4, 42))
