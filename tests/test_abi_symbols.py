@@ -56,3 +56,31 @@ def test_mlp_describe_matches_the_reference_layer_structure(libpath):
     v = NetDesc(8, [4], 63, 27, 4)
     assert v.n_layers == 10
     assert v.w_bytes == d.w_bytes + 2 * (256 * 256 + 128 * (256 + 32)) + 2 * 256 * 16
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every prototype of include/ctxnerf.h has as many parameters, and pointers / 64-bit integers in the same
+    positions, as the ctypes signature the Python host binds it with."""
+    from ctxnerf import _lib
+    text = open(os.path.join(ROOT, "include", "ctxnerf.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"\b(?:int|const char\*)\s+(ctx_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", text, flags=re.S)
+    assert len(protos) >= 20
+    for name, args in protos:
+        args = " ".join(args.split())
+        params = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+        _, argtypes = _lib._SIGNATURES[name]
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+        for p, t in zip(params, argtypes):
+            if "*" in p:
+                assert t is ctypes.c_void_p or t is ctypes.c_char_p, (name, p, t)
+            elif p.startswith("int64_t"):
+                assert t is ctypes.c_int64, (name, p, t)
+            elif p.startswith("uint64_t"):
+                assert t is ctypes.c_uint64, (name, p, t)
+            elif p.startswith("uint32_t"):
+                assert t in (ctypes.c_uint32, ctypes.c_int), (name, p, t)
+            elif p.startswith("float"):
+                assert t is ctypes.c_float, (name, p, t)
+            elif p.startswith("int "):
+                assert t is ctypes.c_int, (name, p, t)
