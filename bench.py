@@ -392,7 +392,9 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": CONFIG, "clocks": clocks,
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": RAYS_PER_GPU * (8 + 12),
-                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                    "host_loop": "NerfTrainer.step_from_host per step (pinned ray ids + targets in, loss out); the host "
+                                 "reads step i's loss after submitting step i+1, the last one inside the timed region"},
             "gpu_launches": launches, "roofline": roofline,
             "step_tensor_frac": step_flops / (ms / args.steps * 1e-3) / 1e12 / pk["tf_sustained"],
             "step_hbm_frac": (REC_BYTES_PER_POINT["fwd"] + REC_BYTES_PER_POINT["dgrad"] + WGRAD_BYTES_PER_POINT)
