@@ -147,7 +147,8 @@ __global__ void __launch_bounds__(kRayWarps * 32) raygen_kernel(RaygenParams p) 
   }
   for (int64_t r = warp0; r < p.n_rays; r += nwarps) {
     const int64_t pix = p.ray_idx ? p.ray_idx[r] : r;
-    const int py = (int)(pix / p.W), px = (int)(pix - (int64_t)py * p.W);
+    const uint32_t pix32 = (uint32_t)pix;                       // H*W < 2^31 is checked by the launcher
+    const int py = (int)(pix32 / (uint32_t)p.W), px = (int)(pix32 - (uint32_t)py * (uint32_t)p.W);
     const float a = ((float)px - p.cx) / p.fx;
     const float b = -((float)py - p.cy) / p.fy;
     const float c = -1.0f;
@@ -269,6 +270,7 @@ extern "C" int ctx_raygen_fwd(int H, int W, float fx, float fy, float cx, float 
                               float* rays_o, float* rays_d, float* viewdirs, float* z_vals,
                               float* near_far, void* stream) {
   if (H < 1 || W < 1 || n_rays < 0 || !c2w || c2w_ld < 4 || n_samples < 0) return CTX_ERR_BAD_ARG;
+  if ((int64_t)H * W >= ((int64_t)1 << 31)) return CTX_ERR_BAD_ARG;   // pixel ids are split with 32-bit arithmetic
   if (n_rays == 0) return 0;
   if (!rays_o || !rays_d) return CTX_ERR_BAD_ARG;
   if (use_sphere && !sphere) return CTX_ERR_BAD_ARG;
