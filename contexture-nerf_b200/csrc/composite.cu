@@ -25,13 +25,20 @@ __device__ __forceinline__ SampleTerms sample_terms(float sigma, float dist) {
   return t;
 }
 
-// inclusive product scan across the warp
-__device__ __forceinline__ float warp_scan_prod(float v, int lane) {
+// inclusive product scan across a group of G consecutive lanes (`lane` = position inside the group)
+template <int G>
+__device__ __forceinline__ float group_scan_prod(float v, int lane) {
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const float n = __shfl_up_sync(CTX_FULL_MASK, v, o);
+  for (int o = 1; o < G; o <<= 1) {
+    const float n = __shfl_up_sync(CTX_FULL_MASK, v, o, G);
     if (lane >= o) v *= n;
   }
+  return v;
+}
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(CTX_FULL_MASK, v, o, G);
   return v;
 }
 
@@ -77,22 +84,28 @@ __device__ __forceinline__ void store_row(float* __restrict__ p, int64_t base, i
   }
 }
 
-template <int K>
+// G lanes share a ray (32 / G rays per warp): short rays use 8- or 16-lane groups so that the scan and the five
+// reductions, the part of the work that does not shrink with S, are paid once per 4 or 2 rays.
+template <int K, int G>
 __global__ void __launch_bounds__(kCompWarps * 32)
 composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z,
                      const float* __restrict__ rays_d, const float* __restrict__ noise,
-                     int64_t R, int S, int vec, int white_bkgd,
+                     int64_t R, int S_all, int vec, int white_bkgd,
                      float* __restrict__ rgb_map, float* __restrict__ disp_map,
                      float* __restrict__ acc_map, float* __restrict__ weights,
                      float* __restrict__ depth_map) {
-  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / G;                        // rays per warp
+  const int lane = threadIdx.x & (G - 1), sub = (threadIdx.x & 31) / G;
   const int64_t warp0 = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kCompWarps;
   const int s0 = lane * K;
-  for (int64_t ray = warp0; ray < R; ray += nwarps) {
+  for (int64_t rb = warp0 * RPW; rb < R; rb += nwarps * RPW) {
+    const bool live = rb + sub < R;                  // lane groups past the last ray only take part in the shuffles
+    const int64_t ray = live ? rb + sub : R - 1;
+    const int S = live ? S_all : 0;
     const float dx = rays_d[ray * 3 + 0], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
     const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
-    const int64_t base = ray * S;
+    const int64_t base = ray * S_all;
     float4 rw[K];
     float zl[K + 1], nz[K + 1];
     // every load of the ray is issued up front
@@ -105,7 +118,7 @@ composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
 #pragma unroll
       for (int k = 0; k < K; ++k) nz[k] = 0.f;
     }
-    zl[K] = __shfl_down_sync(CTX_FULL_MASK, zl[0], 1);   // first depth of the next lane
+    zl[K] = __shfl_down_sync(CTX_FULL_MASK, zl[0], 1, G);   // first depth of the next lane
     // serial pass: alpha and the transmittance prefix inside the lane
     float al[K], pref[K];
     float run = 1.0f;
@@ -119,8 +132,8 @@ composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
       pref[k] = run;
       run *= ok ? t.trans_factor : 1.0f;
     }
-    const float incl = warp_scan_prod(run, lane);
-    float excl = __shfl_up_sync(CTX_FULL_MASK, incl, 1);
+    const float incl = group_scan_prod<G>(run, lane);
+    float excl = __shfl_up_sync(CTX_FULL_MASK, incl, 1, G);
     if (lane == 0) excl = 1.0f;
     float w[K];
     float sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f;
@@ -136,8 +149,8 @@ composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
       }
     }
     store_row<K>(weights, base, s0, S, vec, w);
-    sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sd = warp_sum(sd); sa = warp_sum(sa);
-    if (lane == 0) {
+    sr = group_sum<G>(sr); sg = group_sum<G>(sg); sb = group_sum<G>(sb); sd = group_sum<G>(sd); sa = group_sum<G>(sa);
+    if (lane == 0 && live) {
       const float bg = white_bkgd ? (1.0f - sa) : 0.0f;
       rgb_map[ray * 3 + 0] = sr + bg;
       rgb_map[ray * 3 + 1] = sg + bg;
@@ -157,22 +170,26 @@ composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
 // by t_i, which is 1e-10 at an opaque sample -- SURVEY.md H5).  S_i = U_{i+1} with
 // U_j = b_j + a_j U_{j+1}, a_j = t_j, b_j = G_j alpha_j: composed inside the lane, scanned across lanes, and
 // substituted back.
-template <int K>
+template <int K, int G>
 __global__ void __launch_bounds__(kCompWarps * 32)
 composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z,
                      const float* __restrict__ rays_d, const float* __restrict__ noise,
-                     int64_t R, int S, int vec, int white_bkgd,
+                     int64_t R, int S_all, int vec, int white_bkgd,
                      const float* __restrict__ g_rgb, const float* __restrict__ g_disp,
                      const float* __restrict__ g_acc, const float* __restrict__ g_weights,
                      const float* __restrict__ g_depth, float4* __restrict__ g_raw) {
-  const int lane = threadIdx.x & 31;
+  constexpr int RPW = 32 / G;
+  const int lane = threadIdx.x & (G - 1), sub = (threadIdx.x & 31) / G;
   const int64_t warp0 = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kCompWarps;
   const int s0 = lane * K;
-  for (int64_t ray = warp0; ray < R; ray += nwarps) {
+  for (int64_t rb = warp0 * RPW; rb < R; rb += nwarps * RPW) {
+    const bool live = rb + sub < R;
+    const int64_t ray = live ? rb + sub : R - 1;
+    const int S = live ? S_all : 0;
     const float dx = rays_d[ray * 3 + 0], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
     const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
-    const int64_t base = ray * S;
+    const int64_t base = ray * S_all;
     float4 rw[K];
     float zl[K + 1], nz[K + 1], gw[K + 1];
 #pragma unroll
@@ -189,7 +206,7 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
 #pragma unroll
       for (int k = 0; k < K; ++k) gw[k] = 0.f;
     }
-    zl[K] = __shfl_down_sync(CTX_FULL_MASK, zl[0], 1);
+    zl[K] = __shfl_down_sync(CTX_FULL_MASK, zl[0], 1, G);
     // forward recompute: expo (alpha, t follow from it), the in-lane transmittance prefix, the ray totals
     float ex[K], dist[K], pref[K];
     float run = 1.0f;
@@ -203,8 +220,8 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
       pref[k] = run;
       run *= ok ? t.trans_factor : 1.0f;
     }
-    const float incl = warp_scan_prod(run, lane);
-    float excl = __shfl_up_sync(CTX_FULL_MASK, incl, 1);
+    const float incl = group_scan_prod<G>(run, lane);
+    float excl = __shfl_up_sync(CTX_FULL_MASK, incl, 1, G);
     if (lane == 0) excl = 1.0f;
     float sd = 0.f, sa = 0.f;
 #pragma unroll
@@ -215,7 +232,7 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
         sa += w;
       }
     }
-    sd = warp_sum(sd); sa = warp_sum(sa);
+    sd = group_sum<G>(sd); sa = group_sum<G>(sa);
     const float gr = g_rgb ? g_rgb[ray * 3 + 0] : 0.f;
     const float gg = g_rgb ? g_rgb[ray * 3 + 1] : 0.f;
     const float gb = g_rgb ? g_rgb[ray * 3 + 2] : 0.f;
@@ -234,31 +251,31 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
     }
     if (white_bkgd) ga -= (gr + gg + gb);
     // G_k, and the lane's composed map U_first = Bc + A * U_(first sample of the next lane)
-    float G[K];
+    float Gs[K];
     float A = 1.0f, Bc = 0.f;
 #pragma unroll
     for (int k = K - 1; k >= 0; --k) {
       const bool ok = s0 + k < S;
       const float cr = sigmoidf_(rw[k].x), cg = sigmoidf_(rw[k].y), cb = sigmoidf_(rw[k].z);
-      G[k] = gw[k] + gr * cr + gg * cg + gb * cb + gd * zl[k] + ga;
+      Gs[k] = gw[k] + gr * cr + gg * cg + gb * cb + gd * zl[k] + ga;
       const float alpha = 1.0f - ex[k];
       const float a = ok ? ((1.0f - alpha) + 1e-10f) : 1.0f;
-      const float b = ok ? G[k] * alpha : 0.f;
+      const float b = ok ? Gs[k] * alpha : 0.f;
       Bc = b + a * Bc;
       A = a * A;
     }
     {
       float a = A, b = Bc;   // inclusive suffix scan over the lanes: (a, b) <- map of lanes [lane, 32)
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const float a2 = __shfl_down_sync(CTX_FULL_MASK, a, o);
-        const float b2 = __shfl_down_sync(CTX_FULL_MASK, b, o);
-        if (lane + o < 32) { b = b + a * b2; a = a * a2; }
+      for (int o = 1; o < G; o <<= 1) {
+        const float a2 = __shfl_down_sync(CTX_FULL_MASK, a, o, G);
+        const float b2 = __shfl_down_sync(CTX_FULL_MASK, b, o, G);
+        if (lane + o < G) { b = b + a * b2; a = a * a2; }
       }
       Bc = b;                // = U of this lane's first sample (U past the end of the ray is 0)
     }
-    float U = __shfl_down_sync(CTX_FULL_MASK, Bc, 1);
-    if (lane == 31) U = 0.f;
+    float U = __shfl_down_sync(CTX_FULL_MASK, Bc, 1, G);
+    if (lane == G - 1) U = 0.f;
 #pragma unroll
     for (int k = K - 1; k >= 0; --k) {
       const bool ok = s0 + k < S;
@@ -266,7 +283,7 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
       const float T = excl * pref[k];
       if (ok) {
         const float cr = sigmoidf_(rw[k].x), cg = sigmoidf_(rw[k].y), cb = sigmoidf_(rw[k].z);
-        const float g_alpha = T * (G[k] - U);
+        const float g_alpha = T * (Gs[k] - U);
         const float sig = rw[k].w + nz[k];
         const float g_sigma = (sig > 0.f) ? g_alpha * ex[k] * dist[k] : 0.f;
         const float w = alpha * T;
@@ -276,7 +293,7 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
         o4.z = w * gb * cb * (1.0f - cb);
         o4.w = g_sigma;
         g_raw[base + s0 + k] = o4;
-        U = G[k] * alpha + ((1.0f - alpha) + 1e-10f) * U;
+        U = Gs[k] * alpha + ((1.0f - alpha) + 1e-10f) * U;
       }
     }
   }
@@ -293,8 +310,9 @@ static inline int comp_vec(int S, std::initializer_list<const void*> ptrs) {
   return vec;
 }
 
-static inline int comp_grid(int64_t R) {
-  int64_t blocks = ceil_div(R, kCompWarps);
+static inline int comp_grid(int64_t R, int S) {
+  const int rpw = S <= 32 ? 4 : (S <= 64 ? 2 : 1);   // rays per warp of the dispatch below
+  int64_t blocks = ceil_div(R, (int64_t)kCompWarps * rpw);
   const int64_t cap = (int64_t)kNumSMs * 8;  // 8 CTAs of 8 warps = 64 warps/SM, grid-stride beyond
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
@@ -303,16 +321,16 @@ static inline int comp_grid(int64_t R) {
 
 }  // namespace ctx
 
-// K = samples per lane (S <= 32 K)
-#define CTX_COMP_DISPATCH(KERNEL, ...)                                                   \
-  if (S <= 32) KERNEL<1><<<grid, block, 0, st>>>(__VA_ARGS__);                          \
-  else if (S <= 64) KERNEL<2><<<grid, block, 0, st>>>(__VA_ARGS__);                     \
-  else if (S <= 96) KERNEL<3><<<grid, block, 0, st>>>(__VA_ARGS__);                     \
-  else if (S <= 128) KERNEL<4><<<grid, block, 0, st>>>(__VA_ARGS__);                    \
-  else if (S <= 192) KERNEL<6><<<grid, block, 0, st>>>(__VA_ARGS__);                    \
-  else if (S <= 256) KERNEL<8><<<grid, block, 0, st>>>(__VA_ARGS__);                    \
-  else if (S <= 384) KERNEL<12><<<grid, block, 0, st>>>(__VA_ARGS__);                   \
-  else KERNEL<16><<<grid, block, 0, st>>>(__VA_ARGS__);
+// K = samples per lane, G = lanes per ray (S <= G K)
+#define CTX_COMP_DISPATCH(KERNEL, ...)                                                      \
+  if (S <= 32) KERNEL<4, 8><<<grid, block, 0, st>>>(__VA_ARGS__);                          \
+  else if (S <= 64) KERNEL<4, 16><<<grid, block, 0, st>>>(__VA_ARGS__);                    \
+  else if (S <= 96) KERNEL<3, 32><<<grid, block, 0, st>>>(__VA_ARGS__);                    \
+  else if (S <= 128) KERNEL<4, 32><<<grid, block, 0, st>>>(__VA_ARGS__);                   \
+  else if (S <= 192) KERNEL<6, 32><<<grid, block, 0, st>>>(__VA_ARGS__);                   \
+  else if (S <= 256) KERNEL<8, 32><<<grid, block, 0, st>>>(__VA_ARGS__);                   \
+  else if (S <= 384) KERNEL<12, 32><<<grid, block, 0, st>>>(__VA_ARGS__);                  \
+  else KERNEL<16, 32><<<grid, block, 0, st>>>(__VA_ARGS__);
 
 extern "C" int ctx_composite_fwd(const float* raw, const float* z_vals, const float* rays_d,
                                  const float* noise, int64_t R, int S, int white_bkgd,
@@ -323,7 +341,7 @@ extern "C" int ctx_composite_fwd(const float* raw, const float* z_vals, const fl
   if (!raw || !z_vals || !rays_d || !rgb_map || !disp_map || !acc_map || !weights || !depth_map)
     return CTX_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = ctx::comp_grid(R), block = ctx::kCompWarps * 32;
+  const int grid = ctx::comp_grid(R, S), block = ctx::kCompWarps * 32;
   const int vec = ctx::comp_vec(S, {z_vals, noise, weights});
   CTX_COMP_DISPATCH(ctx::composite_fwd_kernel, (const float4*)raw, z_vals, rays_d, noise, R, S, vec,
                     white_bkgd, rgb_map, disp_map, acc_map, weights, depth_map)
@@ -339,7 +357,7 @@ extern "C" int ctx_composite_bwd(const float* raw, const float* z_vals, const fl
   if (R == 0) return 0;
   if (!raw || !z_vals || !rays_d || !g_raw) return CTX_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = ctx::comp_grid(R), block = ctx::kCompWarps * 32;
+  const int grid = ctx::comp_grid(R, S), block = ctx::kCompWarps * 32;
   const int vec = ctx::comp_vec(S, {z_vals, noise, g_weights});
   CTX_COMP_DISPATCH(ctx::composite_bwd_kernel, (const float4*)raw, z_vals, rays_d, noise, R, S, vec,
                     white_bkgd, g_rgb, g_disp, g_acc, g_weights, g_depth, (float4*)g_raw)
