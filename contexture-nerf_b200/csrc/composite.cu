@@ -313,7 +313,7 @@ static inline int comp_vec(int S, std::initializer_list<const void*> ptrs) {
 static inline int comp_grid(int64_t R, int S) {
   const int rpw = S <= 32 ? 4 : (S <= 64 ? 2 : 1);   // rays per warp of the dispatch below
   int64_t blocks = ceil_div(R, (int64_t)kCompWarps * rpw);
-  const int64_t cap = (int64_t)kNumSMs * 8;  // 8 CTAs of 8 warps = 64 warps/SM, grid-stride beyond
+  const int64_t cap = (int64_t)num_sms() * 8;  // 8 CTAs of 8 warps = 64 warps/SM, grid-stride beyond
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
@@ -340,6 +340,7 @@ extern "C" int ctx_composite_fwd(const float* raw, const float* z_vals, const fl
   if (R == 0) return 0;
   if (!raw || !z_vals || !rays_d || !rgb_map || !disp_map || !acc_map || !weights || !depth_map)
     return CTX_ERR_BAD_ARG;
+  if (reinterpret_cast<uintptr_t>(raw) % 16 != 0) return CTX_ERR_BAD_ARG;   // raw is read as float4 (128-bit loads)
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ctx::comp_grid(R, S), block = ctx::kCompWarps * 32;
   const int vec = ctx::comp_vec(S, {z_vals, noise, weights});
@@ -356,6 +357,8 @@ extern "C" int ctx_composite_bwd(const float* raw, const float* z_vals, const fl
   if (R < 0 || S < 1 || S > 512) return CTX_ERR_BAD_ARG;
   if (R == 0) return 0;
   if (!raw || !z_vals || !rays_d || !g_raw) return CTX_ERR_BAD_ARG;
+  if (reinterpret_cast<uintptr_t>(raw) % 16 != 0 || reinterpret_cast<uintptr_t>(g_raw) % 16 != 0)
+    return CTX_ERR_BAD_ARG;                                                  // float4 loads / stores
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ctx::comp_grid(R, S), block = ctx::kCompWarps * 32;
   const int vec = ctx::comp_vec(S, {z_vals, noise, g_weights});

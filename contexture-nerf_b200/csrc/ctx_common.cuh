@@ -19,7 +19,20 @@
 
 namespace ctx {
 
-constexpr int kNumSMs = 148;  // B200
+constexpr int kNumSMs = 148;  // B200 (compile-time sizing of job tables); launch geometry uses num_sms()
+
+// SM count of the current device (cached per device): grids and SM budgets follow the part the code runs on
+inline int num_sms() {
+  static int cached[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return kNumSMs;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -339,7 +339,7 @@ int ctx_launch_dgrad(const CtxMlpNet& net, const void* wtpacked, const float* fp
     if (e != cudaSuccess) return (int)e;
   }
   const int64_t citers = ctx::ceil_div(P, (int64_t)ctx::kTileM * 4);
-  int cap = ctx::kNumSMs / 2;   // one cluster per SM pair; a smaller SM budget leaves room for a concurrent kernel
+  int cap = ctx::num_sms() / 2;   // one cluster per SM pair; a smaller SM budget leaves room for a concurrent kernel
   if (max_sms > 0 && max_sms / 2 < cap) cap = max_sms / 2;
   if (cap < 1) cap = 1;
   const int ncl = (int)(citers < cap ? citers : cap);

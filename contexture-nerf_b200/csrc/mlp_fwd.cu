@@ -559,7 +559,7 @@ extern "C" int ctx_mlp_fwd(const void* net_host, const void* wpacked, const floa
   cudaError_t e = cudaMemsetAsync(out, 0, (size_t)P * a.net.out_ch * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
   const int64_t citers = ctx::ceil_div(P, (int64_t)ctx::kTileM * 4);
-  const int ncl = (int)(citers < ctx::kNumSMs / 2 ? citers : ctx::kNumSMs / 2);
+  const int ncl = (int)(citers < ctx::num_sms() / 2 ? citers : ctx::num_sms() / 2);
   kernels[(a.prof ? 2 : 0) + (a.acts ? 1 : 0)]<<<2 * ncl, ctx::kMlpThreads, ctx::kMlp2SmemBytes, st>>>(a);
   CTX_RETURN_LAST();
 }

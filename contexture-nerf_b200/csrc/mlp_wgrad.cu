@@ -308,8 +308,8 @@ extern "C" int ctx_mlp_wgrad_ex(const void* net_host, const void* acts, const vo
     // distribute the 148 CTAs over the jobs proportionally to their HBM traffic
     float total = 0.f;
     for (int j = 0; j < nj; ++j) total += cost[j];
-    int budget = ctx::kNumSMs, begin = 0;
-    const bool capped = max_sms > 0 && max_sms < ctx::kNumSMs;
+    int budget = ctx::num_sms(), begin = 0;
+    const bool capped = max_sms > 0 && max_sms < ctx::num_sms();
     if (capped) budget = max_sms & ~1;
     if (budget < 2 * nj) return CTX_ERR_UNSUPPORTED;
     int given[ctx::kWgMaxJobs];

@@ -73,7 +73,7 @@ extern "C" int ctx_tanh01_fwd(const float* raw, float* out, int64_t P, int C, vo
   if (P < 0 || C < 1 || !raw || !out) return CTX_ERR_BAD_ARG;
   if (P == 0) return 0;
   int64_t blocks = ctx::ceil_div(P, 256);
-  if (blocks > ctx::kNumSMs * 8) blocks = ctx::kNumSMs * 8;
+  if (blocks > ctx::num_sms() * 8) blocks = ctx::num_sms() * 8;
   ctx::tanh01_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(raw, out, P, C);
   CTX_RETURN_LAST();
 }
@@ -83,7 +83,7 @@ extern "C" int ctx_tanh01_bwd(const float* raw, const float* g_tex, const float*
   if (P < 0 || C < 1 || !raw || !g_raw) return CTX_ERR_BAD_ARG;
   if (P == 0) return 0;
   int64_t blocks = ctx::ceil_div(P, 256);
-  if (blocks > ctx::kNumSMs * 8) blocks = ctx::kNumSMs * 8;
+  if (blocks > ctx::num_sms() * 8) blocks = ctx::num_sms() * 8;
   ctx::tanh01_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(raw, g_tex, g_raw_in, g_raw, P, C);
   CTX_RETURN_LAST();
 }
@@ -96,7 +96,7 @@ extern "C" int ctx_adam_step(float* params, const float* grads, float* exp_avg, 
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2 = sqrtf(1.f - powf(beta2, (float)step));
   int64_t blocks = ctx::ceil_div(n, 256);
-  if (blocks > ctx::kNumSMs * 8) blocks = ctx::kNumSMs * 8;
+  if (blocks > ctx::num_sms() * 8) blocks = ctx::num_sms() * 8;
   ctx::adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1,
                                                                   beta2, eps, bc1, bc2, weight_decay, grad_scale);
   CTX_RETURN_LAST();

@@ -112,7 +112,7 @@ extern "C" int ctx_posenc_fwd(const float* x, float* out, int64_t n, int d, int 
     if (e != cudaSuccess) return (int)e;
   }
   int64_t blocks = ctx::ceil_div(n, ctx::kEncTile);
-  const int64_t cap = (int64_t)ctx::kNumSMs * 12;
+  const int64_t cap = (int64_t)ctx::num_sms() * 12;
   if (blocks > cap) blocks = cap;
   cudaStream_t st = (cudaStream_t)stream;
   const int inc = include_input ? 1 : 0;
@@ -138,7 +138,7 @@ extern "C" int ctx_posenc_bwd(const float* x, const float* g_out, float* g_x, in
     if (e != cudaSuccess) return (int)e;
   }
   int64_t blocks = ctx::ceil_div(n, ctx::kEncTile);
-  const int64_t cap = (int64_t)ctx::kNumSMs * 12;
+  const int64_t cap = (int64_t)ctx::num_sms() * 12;
   if (blocks > cap) blocks = cap;
   ctx::posenc_bwd_kernel<<<(int)blocks, ctx::kEncThreads, smem, (cudaStream_t)stream>>>(
       x, g_out, g_x, n, d, L, include_input ? 1 : 0, log_sampling);

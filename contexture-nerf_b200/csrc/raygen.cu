@@ -254,7 +254,7 @@ __global__ void ndc_bwd_kernel(int H, int W, float focal, float near, const floa
 
 static inline int warp_grid(int64_t rows, int warps_per_cta) {
   int64_t blocks = ceil_div(rows, warps_per_cta);
-  const int64_t cap = (int64_t)kNumSMs * 8;
+  const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
@@ -304,7 +304,7 @@ extern "C" int ctx_ndc_fwd(int H, int W, float focal, float near, const float* r
   if (n < 0 || !rays_o || !rays_d || !o_out || !d_out) return CTX_ERR_BAD_ARG;
   if (n == 0) return 0;
   int64_t blocks = ctx::ceil_div(n, 256);
-  if (blocks > ctx::kNumSMs * 8) blocks = ctx::kNumSMs * 8;
+  if (blocks > ctx::num_sms() * 8) blocks = ctx::num_sms() * 8;
   ctx::ndc_fwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(H, W, focal, near, rays_o, rays_d,
                                                                     n, o_out, d_out);
   CTX_RETURN_LAST();
@@ -316,7 +316,7 @@ extern "C" int ctx_ndc_bwd(int H, int W, float focal, float near, const float* r
   if (n < 0 || !rays_o || !rays_d || !g_rays_o || !g_rays_d) return CTX_ERR_BAD_ARG;
   if (n == 0) return 0;
   int64_t blocks = ctx::ceil_div(n, 256);
-  if (blocks > ctx::kNumSMs * 8) blocks = ctx::kNumSMs * 8;
+  if (blocks > ctx::num_sms() * 8) blocks = ctx::num_sms() * 8;
   ctx::ndc_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(H, W, focal, near, rays_o, rays_d,
                                                                     g_o, g_d, n, g_rays_o, g_rays_d);
   CTX_RETURN_LAST();

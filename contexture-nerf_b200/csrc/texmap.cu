@@ -161,7 +161,7 @@ static inline bool texmap_vec_ok(int64_t N, int C, std::initializer_list<const v
 
 static inline int texmap_grid(int64_t total) {
   int64_t blocks = ceil_div(total, 256);
-  const int64_t cap = (int64_t)kNumSMs * 8;
+  const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
   return (int)(blocks < 1 ? 1 : blocks);
 }

@@ -44,42 +44,56 @@ class NetDesc:
 
 
 class PackedWeights:
-    """bf16 weight streams (forward + transposed) and the fp32 bias/head block,
-    per device; re-packed when any parameter's version counter changes
-    (optimizer steps bump it)."""
+    """bf16 weight streams (forward + transposed) and the fp32 bias/head block, per device.
+
+    Cache discipline: an entry is keyed on the IDENTITY of the parameter tensors (``id`` of live leaf
+    ``nn.Parameter`` objects, held by weak reference so that a recycled id cannot alias) plus their ``_version``
+    counters, never on addresses.  Non-leaf parameters -- the per-iteration replicas ``nn.DataParallel`` broadcasts
+    (/root/reference/src/training/trainer.py:134-135) -- are always re-packed.  Every pack writes FRESH buffers:
+    a saved autograd graph keeps the buffers it ran with (``ctx.packed``), so a later re-pack (forward A, optimizer
+    step, forward B, backward A) cannot change the transposed weights under a pending backward."""
 
     def __init__(self, desc: NetDesc):
         self.desc = desc
         self._per_dev = {}
+        self.generation = 0          # number of packs performed (monotone; tests and the trainer read it)
 
     def invalidate(self):
         """Force a re-pack (parameters were updated in place by a non-torch kernel)."""
-        for dev in list(self._per_dev):
-            self._per_dev[dev] = (None, self._per_dev[dev][1])
+        self._per_dev.clear()
 
     def get(self, params: List[torch.Tensor]):
+        import weakref
         dev = params[0].device
-        key = tuple((p.data_ptr(), p._version) for p in params)
-        ent = self._per_dev.get(dev)
-        if ent is not None and ent[0] == key:
-            return ent[1]
+        cacheable = all(isinstance(p, torch.nn.Parameter) and p.is_leaf for p in params)
+        ent = self._per_dev.get(dev) if cacheable else None
+        if ent is not None:
+            refs, versions, bufs = ent
+            if (len(refs) == len(params) and all(r() is p for r, p in zip(refs, params))
+                    and versions == tuple(p._version for p in params)):
+                return bufs
         d = self.desc
         for p in params:
             if p.dtype != torch.float32 or not p.is_contiguous() or p.device != dev or not p.is_cuda:
                 raise _lib.CtxNerfError("MLP parameters must be contiguous fp32 tensors on one CUDA device "
                                         "(ctxnerf has no CPU path)")
-        if ent is None:
-            bufs = (torch.empty(d.w_bytes, dtype=torch.uint8, device=dev),
-                    torch.empty(max(d.wt_bytes, 16), dtype=torch.uint8, device=dev),
-                    torch.empty(d.n_fparams, dtype=torch.float32, device=dev))
-        else:
-            bufs = ent[1]
-        arr = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
-        with torch.cuda.device(dev):
-            call("ctx_mlp_pack", d.p, ctypes.cast(arr, ctypes.c_void_p), len(params), ptr(bufs[0]), ptr(bufs[1]),
-                 ptr(bufs[2]), stream_ptr(dev))
-        self._per_dev[dev] = (key, bufs)
+        bufs = (torch.empty(d.w_bytes, dtype=torch.uint8, device=dev),
+                torch.empty(max(d.wt_bytes, 16), dtype=torch.uint8, device=dev),
+                torch.empty(d.n_fparams, dtype=torch.float32, device=dev))
+        pack_into(d, params, bufs)
+        self.generation += 1
+        if cacheable:
+            self._per_dev[dev] = (tuple(weakref.ref(p) for p in params), tuple(p._version for p in params), bufs)
         return bufs
+
+
+def pack_into(desc: NetDesc, params: List[torch.Tensor], bufs):
+    """ctx_mlp_pack of ``params`` (reference order) into the given (w, wt, fparams) buffers on the current stream."""
+    dev = params[0].device
+    arr = (ctypes.c_void_p * len(params))(*[p.data_ptr() for p in params])
+    with torch.cuda.device(dev):
+        call("ctx_mlp_pack", desc.p, ctypes.cast(arr, ctypes.c_void_p), len(params), ptr(bufs[0]), ptr(bufs[1]),
+             ptr(bufs[2]), stream_ptr(dev))
 
 
 def _launch_fwd(desc: NetDesc, w, f, *, x=None, rays=None, P: int, out, acts=None, L_pts=10, L_dirs=4):
@@ -107,6 +121,10 @@ def forward_raw(module, *, x=None, rays=None, save_acts=False):
         x = x.reshape(-1, x.shape[-1]).float().contiguous()
         P, dev = x.shape[0], x.device
     else:
+        for t in rays:
+            if t is not None and (not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous()):
+                raise _lib.CtxNerfError("fused ray query needs contiguous fp32 CUDA tensors (rays_o, rays_d, viewdirs, "
+                                        "z_vals); cast with .float().contiguous()")
         z = rays[3]
         P, dev = z.numel(), z.device
     out = torch.empty(P, desc.out_ch, device=dev, dtype=torch.float32)
@@ -124,6 +142,14 @@ class _MlpFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module, x, rays, need_grad, *params):
+        # The kernels differentiate with respect to the parameters only.  An input that asks for a gradient would
+        # silently get none: refuse instead, as loudly as the rest of the package.
+        for t in ((x,) if x is not None else tuple(rays)):
+            if t is not None and t.requires_grad:
+                raise _lib.CtxNerfError(
+                    "ctxnerf MLP: gradients flow to the parameters only; an input (x / rays_o / rays_d / viewdirs / "
+                    "z_vals) has requires_grad=True.  Detach it (upstream never differentiates with respect to rays or "
+                    "encodings) -- learnable coordinates are out of scope (DESIGN.md section 7)")
         lead = x.shape[:-1] if x is not None else rays[3].shape
         out, acts, P, packed = forward_raw(module, x=x, rays=rays, save_acts=need_grad)
         ctx.module, ctx.P, ctx.acts, ctx.packed = module, P, acts, packed
@@ -132,6 +158,8 @@ class _MlpFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_out):
         from .mlp_bwd import mlp_backward
+        if ctx.acts is None:       # nothing asked for a gradient when the forward ran (all parameters frozen)
+            return (None, None, None, None) + tuple(None for _ in ctx.needs_input_grad[4:])
         grads = mlp_backward(ctx.module, ctx.packed, ctx.acts, ctx.P, g_out)
         ctx.acts = None
         return (None, None, None, None) + tuple(grads)

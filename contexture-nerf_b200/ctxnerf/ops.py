@@ -75,6 +75,11 @@ class _Composite(torch.autograd.Function):
     @staticmethod
     def forward(ctx, raw, z_vals, rays_d, noise, white_bkgd):
         _need_cuda(raw, z_vals, rays_d, noise)
+        for name, t in (("z_vals", z_vals), ("rays_d", rays_d), ("noise", noise)):
+            if t is not None and t.requires_grad:
+                raise _lib.CtxNerfError(
+                    f"raw2outputs: the hand-written backward differentiates with respect to raw only; {name} has "
+                    "requires_grad=True and would silently get no gradient.  Detach it (DESIGN.md section 7)")
         raw_c, z_c, d_c, n_c = _f32c(raw), _f32c(z_vals), _f32c(rays_d), _f32c(noise)
         S = raw_c.shape[-2]
         lead = raw_c.shape[:-2]

@@ -35,6 +35,8 @@ def _to_cuda(t, dtype=torch.float32):
         t = torch.as_tensor(np.asarray(t), dtype=dtype)
     if not t.is_cuda:
         t = t.to(_cuda_device())
+    if t.is_floating_point() and t.dtype != dtype:
+        t = t.to(dtype)       # the kernels read float*: a float64 / half batch is converted, never reinterpreted
     return t
 
 
@@ -151,8 +153,9 @@ class NeRF(_FusedMLPBase):
         """Fused query: points o + d*z are formed and encoded inside the MLP
         kernel (nothing but raw [R,S,4] touches HBM)."""
         v = viewdirs if self.use_viewdirs else None
-        return self._run(rays=(rays_o.contiguous(), rays_d.contiguous(),
-                               v.contiguous() if v is not None else None, z_vals.contiguous()))
+        f = _ops._f32c
+        _ops._need_cuda(rays_o, rays_d, v, z_vals)
+        return self._run(rays=(f(rays_o), f(rays_d), f(v), f(z_vals)))
 
 
 # Ray helpers (reference :139-178)
@@ -256,8 +259,8 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     z_vals = _ops.stratified(ray_batch[:, 6], ray_batch[:, 7], N_samples, lindisp=lindisp,
                              perturb=perturb > 0., jitter=jitter)
     fused = isinstance(network_query_fn, FusedQuery) and isinstance(network_fn, NeRF)
-    ro_c, rd_c = rays_o.contiguous(), rays_d.contiguous()
-    vd_c = viewdirs.contiguous() if viewdirs is not None else None
+    ro_c, rd_c = _ops._f32c(rays_o), _ops._f32c(rays_d)
+    vd_c = _ops._f32c(viewdirs)
 
     def query(z, net):
         if fused and isinstance(net, NeRF) and (vd_c is not None or not net.use_viewdirs):

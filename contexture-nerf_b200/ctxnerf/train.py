@@ -18,7 +18,7 @@ import os
 import torch
 
 from . import ops
-from ._lib import call, ptr, stream_ptr
+from ._lib import CtxNerfError, call, ptr, stream_ptr
 from .dist import FlatBucket, world
 from .mlp import forward_raw
 from .mlp_bwd import mlp_backward, mlp_dgrad, mlp_wgrad
@@ -70,9 +70,9 @@ class NerfTrainer:
         self.timers.setdefault(name, []).append((a, b))
         return r
 
-    def _render(self, ray_idx, save_acts, seed):
+    def _render(self, ray_idx, save_acts, seed, perturb):
         S, Ni = self.N_samples, self.N_importance
-        jit = self.perturb > 0.0
+        jit = bool(perturb)
         r = ops.raygen(self.H, self.W, self.K, self.c2w, ray_idx=ray_idx, n_samples=S, near=self.near, far=self.far,
                        lindisp=self.lindisp, perturb=jit, seed=seed, want_viewdirs=True)
         o, d, v, z_c = r["rays_o"], r["rays_d"], r["viewdirs"], r["z_vals"]
@@ -109,7 +109,9 @@ class NerfTrainer:
     def render(self, ray_idx: Optional[torch.Tensor] = None):
         """Inference render of the given pixels (None = the whole H x W image)."""
         with torch.cuda.device(self.device):
-            fwd = self._render(ray_idx, save_acts=False, seed=0)
+            # evaluation is deterministic, as upstream's render_kwargs_test (perturb=False, raw_noise_std=0):
+            # linspace depths and det=True importance sampling; the jitter belongs to step() only
+            fwd = self._render(ray_idx, save_acts=False, seed=0, perturb=False)
         rgb, disp, acc, _, depth = fwd["comp_f"]
         return dict(rgb_map=rgb, disp_map=disp, acc_map=acc, depth_map=depth, rgb0=fwd["comp_c"][0])
 
@@ -131,10 +133,16 @@ class NerfTrainer:
     def step(self, ray_idx: torch.Tensor, target: torch.Tensor, optimizer_step: bool = True) -> torch.Tensor:
         """One training step on this rank's ray batch; returns the loss (device scalar)."""
         dev = self.device
+        if not (torch.is_tensor(target) and target.is_cuda and target.device == dev):
+            raise CtxNerfError("NerfTrainer.step: target must be a CUDA tensor on the trainer's device "
+                               "(use step_from_host for host buffers)")
+        target = ops._f32c(target)
+        if target.numel() != 3 * ray_idx.numel():
+            raise CtxNerfError("NerfTrainer.step: target must hold one rgb triple per ray")
         with torch.cuda.device(dev):
             seed = ops.new_seed() if self.perturb > 0.0 else 0
             self.bucket.zero_grad()
-            f = self._render(ray_idx, save_acts=True, seed=seed)
+            f = self._render(ray_idx, save_acts=True, seed=seed, perturb=self.perturb > 0.0)
             R, S, Sf = f["R"], self.N_samples, self.N_samples + self.N_importance
             g_rgb = torch.empty(R, 3, device=dev)
             g_rgb0 = torch.empty(R, 3, device=dev)

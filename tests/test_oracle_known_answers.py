@@ -4,6 +4,7 @@ so these closed forms are what pins them."""
 import math
 
 import numpy as np
+import pytest
 import torch
 
 from oracle import nerf_oracle as orc
@@ -141,3 +142,48 @@ def test_texture_mapping_restatement():
     mask = torch.tensor([[[1.0], [0.0]]])
     img = orc.render_composite(torch.tensor([[[0.5, 0.5], [0.5, 0.5]]]), tex, mask, 1.0)
     assert img[0, 1, 0].item() == 1.0 and img[0, 0, 0].item() != 1.0
+
+
+# ---------------------------------------------------------------------------------------------------------
+# raw2outputs is unpinned (absent from the reference): cross-check the torch oracle against a second,
+# independently written float64 restatement (oracle/raw2outputs_fp64.py: scalar loops, running transmittance,
+# hand-derived O(S^2) gradient).
+@pytest.mark.parametrize("white", [False, True])
+def test_raw2outputs_agrees_with_independent_fp64_restatement(white):
+    from oracle.raw2outputs_fp64 import raw2outputs_fp64
+    R, S = 24, 40
+    raw, z, d = orc.cfg1_inputs(R, S, seed=3)
+    z = torch.sort(torch.rand(R, S, generator=torch.Generator().manual_seed(4)) * 4 + 2, -1)[0]
+    raw[0, :, 3] = -1.0                   # an empty ray (acc = 0, disp = NaN)
+    raw[1, 7, 3] = 1e4                    # an opaque sample
+    d[2] *= 3.0                           # non-unit direction: distances scale with its norm
+    got = orc.raw2outputs(raw, z, d, white_bkgd=white)
+    ref = raw2outputs_fp64(raw.numpy(), z.numpy(), d.numpy(), white_bkgd=white)
+    for name, a in zip(("rgb", "disp", "acc", "weights", "depth"), got):
+        b = torch.from_numpy(ref[name]).float()
+        if name == "disp":
+            assert torch.equal(torch.isnan(a), torch.isnan(b))
+            ok = ~torch.isnan(b)
+            torch.testing.assert_close(a[ok], b[ok], rtol=2e-5, atol=1e-7)
+        else:
+            # fp32 oracle vs fp64 restatement: rounding of S-term sums / products only
+            torch.testing.assert_close(a, b, rtol=2e-5, atol=2e-6, msg=lambda m: f"{name}: {m}")
+
+
+def test_raw2outputs_gradient_agrees_with_hand_derived_fp64():
+    from oracle.raw2outputs_fp64 import raw2outputs_fp64_backward
+    R, S = 6, 17
+    g = torch.Generator().manual_seed(8)
+    raw = torch.randn(R, S, 4, generator=g, dtype=torch.float64)
+    raw[..., 3] *= 2.0
+    z = torch.sort(torch.rand(R, S, generator=g, dtype=torch.float64) * 4 + 2, -1)[0]
+    d = torch.randn(R, 3, generator=g, dtype=torch.float64)
+    g_rgb, g_acc = torch.randn(R, 3, generator=g, dtype=torch.float64), torch.randn(R, generator=g, dtype=torch.float64)
+    g_w, g_depth = torch.randn(R, S, generator=g, dtype=torch.float64), torch.randn(R, generator=g, dtype=torch.float64)
+    for white in (False, True):
+        r0 = raw.clone().requires_grad_(True)
+        rgb, disp, acc, w, depth = orc.raw2outputs(r0, z, d, white_bkgd=white)      # the oracle runs in any dtype
+        ((rgb * g_rgb).sum() + (acc * g_acc).sum() + (w * g_w).sum() + (depth * g_depth).sum()).backward()
+        ref = raw2outputs_fp64_backward(raw.numpy(), z.numpy(), d.numpy(), g_rgb.numpy(), g_acc.numpy(), g_w.numpy(),
+                                        g_depth.numpy(), white_bkgd=white)
+        torch.testing.assert_close(r0.grad, torch.from_numpy(ref), rtol=1e-9, atol=1e-12)
