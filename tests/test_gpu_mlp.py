@@ -189,10 +189,10 @@ def test_mlp_backward_fused_rays_training_step(cuda):
         cos = torch.nn.functional.cosine_similarity(got, refg, dim=0).item()
         _diag(f"train step {tag}: whole-gradient l2-rel err {l2:.3e}, cosine {cos:.6f}")
         worst_all[tag] = (l2, cos)
-    # bf16 operands end to end (encode -> 10 layers -> compositing -> loss): the gradient direction is what
-    # the optimiser consumes; require cosine >= 0.999 and <= 4 % L2 deviation of the full gradient vector
+    # bf16 operands end to end (encode -> 10 layers -> compositing -> loss): north-star tolerance 2e-2 on the full
+    # gradient vector (measured 1.1e-2 coarse / 1.3e-2 fine) and cosine >= 0.999
     for tag, (l2, cos) in worst_all.items():
-        assert cos > 0.999 and l2 < 0.04, (tag, l2, cos)
+        assert cos > 0.999 and l2 < 0.02, (tag, l2, cos)
 
 
 @pytest.mark.parametrize("res", [64, 200])
