@@ -33,9 +33,9 @@ CONFIG = {"workload": "configs[2]: training step fwd+bwd, 4096-ray batch per GPU
                       "D=8/W=256 view-dir MLPs, L=10/4, gradient all-reduce + Adam",
           "rays_per_gpu": RAYS_PER_GPU, "n_samples": N_SAMPLES, "n_importance": N_IMPORTANCE,
           "image": "800x800 config-2 camera", "perturb": 1.0, "white_bkgd": True,
-          "l2": "no explicit flush: each step streams ~17 GB of activation / dZ records through the 126 MB L2",
-          "schedule": "backward of the coarse network (dgrad -> wgrad) on a side stream beside wgrad of the fine network "
-                      "(SM budgets 44 / 104); one gradient all-reduce"}
+          "l2": "no explicit flush: each step streams ~15 GB of activation / dZ records through the 126 MB L2",
+          "schedule": "one CUDA graph per step (two around the all-reduce when N > 1); backward of the coarse network "
+                      "(dgrad -> wgrad) on a side stream beside wgrad of the fine network (SM budgets 44 / 104)"}
 
 
 def peaks():
@@ -140,14 +140,16 @@ def run_reference(args, rank):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    n_rays = 256
+    # the full 4096-ray batch of the benchmark config (about 5 s per step on 16 cores); --ref-rays bounds it further
+    n_rays = args.ref_rays or RAYS_PER_GPU
     times = cpu_step_sample(n_rays, threads, args.steps, min(args.warmup, 2))
     total = sum(times)
     val = n_rays * len(times) / total
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "rays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(CONFIG, sample=f"{n_rays} rays per step (bounded sample of the 4096-ray batch)"),
+            "config": dict(CONFIG, sample=(f"{n_rays} rays per step" + ("" if n_rays == RAYS_PER_GPU else
+                                                                           " (bounded sample of the 4096-ray batch)"))),
             "cpu_baseline": {"value": val, "unit": "rays/s", "cores": threads, "kind": "port",
                              "sample": f"{n_rays}-ray coarse+fine fwd+bwd step, oracle/nerf_oracle.py (torch CPU fp32), "
                                        f"{len(times)} steps"},
@@ -214,6 +216,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-rays", type=int, default=0,
+                    help="rays per step of the CPU legs (--impl reference / cpu_baseline); default: the full 4096-ray batch")
     ap.add_argument("--cfg1", action="store_true",
                     help="BASELINE configs[0] instead of the training step: raw2outputs(64) -> sample_pdf(det, 128) -> "
                          "merge -> raw2outputs(192) on 4096 rays, GPU chain beside the CPU oracle (parity-test sized)")
@@ -290,8 +294,8 @@ def main():
         timers, tr.timers = tr.timers, None
         return t.item(), clocks, launches, timers
 
-    # ---- device-resident inputs ("value") ----
-    ms, clocks, launches, timers = timed(lambda i: tr.step(idx_d[i % NB], tgt_d[i % NB]), args.steps, True)
+    # ---- device-resident inputs ("value"): the captured step, no per-kernel timers ----
+    ms, clocks, launches, _ = timed(lambda i: tr.step(idx_d[i % NB], tgt_d[i % NB]), args.steps, False)
     value = RAYS_PER_GPU * world * args.steps / (ms * 1e-3)
     # ---- end to end through the public API with host buffers ----
     # Every step copies its ray ids + targets from pinned host memory and its loss is read on the host; the host
@@ -320,29 +324,34 @@ def main():
     final_loss = host_losses[-1]
     loss_h.fill_(final_loss)
 
-    # ---- per-kernel device times -> roofline ----
-    # The timed region overlaps the coarse network's backward chain with wgrad of the fine network (side stream,
-    # disjoint SM budgets), so the kernels' own durations are taken in a short extra pass with the overlap off
-    # ("kernels"), and the dominant PHASE of the timed region -- the concurrent group wgrad_fine || dgrad_coarse ->
-    # wgrad_coarse, timed live with events on the main stream -- is what "roofline" reports.
+    # ---- per-kernel device times -> roofline (two short extra passes, eager launches with event pairs) ----
+    # (1) the schedule of the timed region, with CUDA events around each MLP kernel and around the concurrent backward
+    # group; (2) overlap off: every kernel alone on the whole GPU ("kernels").
     pk = peaks()
+    n_extra = min(args.steps, 6)
+    _, _, _, timers_live = timed(lambda i: tr.step(idx_d[i % NB], tgt_d[i % NB]), n_extra, True)
     group_ms = None
-    if timers and "bwd_overlap_group" in timers:
-        evs = timers["bwd_overlap_group"]
+    if timers_live and "bwd_overlap_group" in timers_live:
+        evs = timers_live["bwd_overlap_group"]
         group_ms = sum(x.elapsed_time(y) for x, y in evs) / len(evs)
     overlap_was = tr.overlap_backward
     tr.overlap_backward = False
-    _, _, _, timers_iso = timed(lambda i: tr.step(idx_d[i % NB], tgt_d[i % NB]), min(args.steps, 6), True)
+    _, _, _, timers_iso = timed(lambda i: tr.step(idx_d[i % NB], tgt_d[i % NB]), n_extra, True)
     tr.overlap_backward = overlap_was
     kern = {}
     for name, evs in (timers_iso or {}).items():
         kern[name] = sum(x.elapsed_time(y) for x, y in evs) / len(evs)
     pts = {"coarse": RAYS_PER_GPU * N_SAMPLES, "fine": RAYS_PER_GPU * (N_SAMPLES + N_IMPORTANCE)}
-    # records per point of the view-direction net: bf16 activations of the 10 GEMM layers
-    # (8 x 256 + 256 + 128 channels), 1-bit ReLU masks, the two encodings; dgrad writes the dZ records of the same
-    # layers + the padded g_out and reads the masks and g_out back
-    REC_BYTES_PER_POINT = {"fwd": 2432 * 2 + 272 + 128 + 64 + 16 + 4, "dgrad": 2432 * 2 + 32 + 272 + 16}
-    WGRAD_BYTES_PER_POINT = 11392.0      # sum over the 14 wgrad jobs of (A + B channels) x 2 B, DESIGN.md section 4
+    # HBM traffic the design generates per evaluated point -- NOT algorithmic bytes: bf16
+    # activation records of the 8 pts layers and the views layer (the linear feature layer keeps none), 1-bit ReLU
+    # masks, the two encodings; dgrad writes the dZ records of the same layers + g_out and reads the masks back; wgrad
+    # streams sum over its 12 jobs of (A + B channels) x 2 B.
+    REC_BYTES_PER_POINT = {"fwd": 2176 * 2 + 272 + 128 + 64 + 16 + 4, "dgrad": 2192 * 2 + 272 + 16,
+                           "wgrad": 9856.0}
+    # algorithmic I/O of one MLP pass per point: z in, raw out (+ g_raw in for the backward kernels);
+    # the 2 x 1.2 MB weight streams / 2 x 2.4 MB gradients per launch are added per launch below
+    ALG_BYTES_PER_POINT = {"fwd": 4 + 16, "dgrad": 16, "wgrad": 0}
+    ALG_BYTES_PER_LAUNCH = {"fwd": 1.2e6, "dgrad": 1.2e6, "wgrad": 2.4e6}
     traffic = {}
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
@@ -353,40 +362,31 @@ def main():
     for name, t_ms in kern.items():
         _, kind, net = name.split("_")
         n = pts[net]
-        if kind == "wgrad":       # HBM-bound: operands are streamed once from the records
-            ach = WGRAD_BYTES_PER_POINT * n / (t_ms * 1e-3) / 1e9
-            kernels[name] = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                             "frac": ach / pk["hbm_gbs"], "ms_per_launch": t_ms}
-        else:                     # fwd / dgrad: one pass of 593 408 MAC per point on the tensor pipe, while the
-            # activation (fwd) / dZ (dgrad) records stream to HBM: both ceilings are reported, the binding one
-            # (larger fraction) names the bound
-            tf = 2.0 * MACS_PER_EVAL * n / (t_ms * 1e-3) / 1e12
-            gb = REC_BYTES_PER_POINT[kind] * n / (t_ms * 1e-3) / 1e9
-            f_t, f_h = tf / pk["tf_sustained"], gb / pk["hbm_gbs"]
-            if f_t >= f_h:
-                kernels[name] = {"bound": "tensor", "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                                 "frac": f_t, "ms_per_launch": t_ms, "hbm_gbs": gb, "hbm_frac": f_h}
-            else:
-                kernels[name] = {"bound": "hbm", "achieved": gb, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                                 "frac": f_h, "ms_per_launch": t_ms, "tensor_tflops": tf, "tensor_frac": f_t}
+        # the MLP is the only dense contraction -> tensor roofline with the algorithmic FLOPs
+        # (593 408 MAC per point per pass; fwd, dgrad and wgrad are one pass each of the 3x rule)
+        tf = 2.0 * MACS_PER_EVAL * n / (t_ms * 1e-3) / 1e12
+        gb = REC_BYTES_PER_POINT[kind] * n / (t_ms * 1e-3) / 1e9
+        alg = ALG_BYTES_PER_POINT[kind] * n + ALG_BYTES_PER_LAUNCH[kind]
+        kernels[name] = {"bound": "tensor", "achieved": tf, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                         "frac": tf / pk["tf_sustained"], "ms_per_launch": t_ms,
+                         "traffic": traffic.get(name), "design_traffic_bytes": REC_BYTES_PER_POINT[kind] * n,
+                         "algorithmic_bytes": alg, "traffic_over_algorithmic": REC_BYTES_PER_POINT[kind] * n / alg,
+                         "hbm_gbs": gb, "hbm_frac": gb / pk["hbm_gbs"]}
     roofline = None
-    if group_ms is not None:
-        gbytes = (WGRAD_BYTES_PER_POINT * pts["fine"] + (REC_BYTES_PER_POINT["dgrad"] + WGRAD_BYTES_PER_POINT) * pts["coarse"])
-        gtraffic = None
-        if all(k in traffic for k in ("mlp_wgrad_fine", "mlp_dgrad_coarse", "mlp_wgrad_coarse")):
-            gtraffic = traffic["mlp_wgrad_fine"] + traffic["mlp_dgrad_coarse"] + traffic["mlp_wgrad_coarse"]
-        ach = gbytes / (group_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"],
-                    "traffic": gtraffic, "ms_per_launch": group_ms,
-                    "kernel": "mlp_wgrad_fine || (mlp_dgrad_coarse -> mlp_wgrad_coarse): concurrent on disjoint SM budgets, "
-                              "timed as one span on the main stream; per-kernel figures (overlap off) under 'kernels'",
-                    "peak_source": pk["source"] + " copy bandwidth"}
-    else:
-        dom = max(kern, key=kern.get) if kern else None
-        if dom:
-            roofline = dict(kernels[dom], kernel=dom, traffic=traffic.get(dom),
-                            peak_source=pk["source"] + (" copy bandwidth" if kernels[dom]["bound"] == "hbm"
-                                                        else " cuBLAS bf16, sustained"))
+    dom = max(kern, key=kern.get) if kern else None
+    if dom:
+        roofline = dict(kernels[dom], kernel=dom + " (timed alone, overlap off; the dominant kernel of the step)",
+                        peak_source=pk["source"] + " cuBLAS bf16, sustained")
+        if group_ms is not None:
+            gbytes = (REC_BYTES_PER_POINT["wgrad"] * pts["fine"]
+                      + (REC_BYTES_PER_POINT["dgrad"] + REC_BYTES_PER_POINT["wgrad"]) * pts["coarse"])
+            gflops = 2.0 * MACS_PER_EVAL * (pts["fine"] + 2 * pts["coarse"])
+            roofline["concurrent_group"] = {
+                "what": "mlp_wgrad_fine || (mlp_dgrad_coarse -> mlp_wgrad_coarse), disjoint SM budgets, one span on the "
+                        "main stream, measured live in the schedule of the timed region",
+                "ms": group_ms, "tensor_tflops": gflops / (group_ms * 1e-3) / 1e12,
+                "tensor_frac": gflops / (group_ms * 1e-3) / 1e12 / pk["tf_sustained"],
+                "hbm_gbs": gbytes / (group_ms * 1e-3) / 1e9, "hbm_frac": gbytes / (group_ms * 1e-3) / 1e9 / pk["hbm_gbs"]}
     step_flops = 3 * 2.0 * MACS_PER_EVAL * RAYS_PER_GPU * EVALS_PER_RAY
     line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -397,13 +397,13 @@ def main():
                                  "reads step i's loss after submitting step i+1, the last one inside the timed region"},
             "gpu_launches": launches, "roofline": roofline,
             "step_tensor_frac": step_flops / (ms / args.steps * 1e-3) / 1e12 / pk["tf_sustained"],
-            "step_hbm_frac": (REC_BYTES_PER_POINT["fwd"] + REC_BYTES_PER_POINT["dgrad"] + WGRAD_BYTES_PER_POINT)
+            "step_hbm_frac": (REC_BYTES_PER_POINT["fwd"] + REC_BYTES_PER_POINT["dgrad"] + REC_BYTES_PER_POINT["wgrad"])
             * RAYS_PER_GPU * EVALS_PER_RAY / (ms / args.steps * 1e-3) / 1e9 / pk["hbm_gbs"],
             "kernels": kernels, "final_loss": final_loss}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            n = 256
+            n = args.ref_rays or RAYS_PER_GPU
             times = cpu_step_sample(n, threads, 3, 1)
             line["cpu_baseline"] = {"value": n * len(times) / sum(times), "unit": "rays/s", "cores": threads,
                                     "kind": "port",

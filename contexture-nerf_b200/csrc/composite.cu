@@ -170,14 +170,22 @@ composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
 // by t_i, which is 1e-10 at an opaque sample -- SURVEY.md H5).  S_i = U_{i+1} with
 // U_j = b_j + a_j U_{j+1}, a_j = t_j, b_j = G_j alpha_j: composed inside the lane, scanned across lanes, and
 // substituted back.
-template <int K, int G>
+//
+// TRAIN = true is the fused training form (NerfTrainer.step): the forward the backward has to recompute anyway
+// also yields rgb_map, so the photometric loss img2mse(rgb_map, target) (src/run_nerf_helpers.py:9) and its
+// gradient g_rgb = 2 (rgb_map - target) * loss_scale are formed in place -- one pass over raw replaces
+// composite_fwd + mse + composite_bwd.  It writes g_raw, optionally weights (the coarse pass feeds sample_pdf) and
+// rgb_map, and adds sum((rgb-target)^2) * loss_scale into loss[0] (one atomic per warp pass).
+template <int K, int G, bool TRAIN>
 __global__ void __launch_bounds__(kCompWarps * 32)
 composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z,
                      const float* __restrict__ rays_d, const float* __restrict__ noise,
                      int64_t R, int S_all, int vec, int white_bkgd,
                      const float* __restrict__ g_rgb, const float* __restrict__ g_disp,
                      const float* __restrict__ g_acc, const float* __restrict__ g_weights,
-                     const float* __restrict__ g_depth, float4* __restrict__ g_raw) {
+                     const float* __restrict__ g_depth, float4* __restrict__ g_raw,
+                     const float* __restrict__ target, float loss_scale, float* __restrict__ loss,
+                     float* __restrict__ weights_out, float* __restrict__ rgb_out) {
   constexpr int RPW = 32 / G;
   const int lane = threadIdx.x & (G - 1), sub = (threadIdx.x & 31) / G;
   const int64_t warp0 = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
@@ -201,7 +209,7 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
 #pragma unroll
       for (int k = 0; k < K; ++k) nz[k] = 0.f;
     }
-    if (g_weights != nullptr) load_row<K>(g_weights, base, s0, S, vec, gw);
+    if (!TRAIN && g_weights != nullptr) load_row<K>(g_weights, base, s0, S, vec, gw);
     else {
 #pragma unroll
       for (int k = 0; k < K; ++k) gw[k] = 0.f;
@@ -224,21 +232,53 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
     float excl = __shfl_up_sync(CTX_FULL_MASK, incl, 1, G);
     if (lane == 0) excl = 1.0f;
     float sd = 0.f, sa = 0.f;
+    float gr, gg, gb, gd, ga, gdisp;
+    if constexpr (TRAIN) {
+      float sr = 0.f, sg = 0.f, sb = 0.f;
+      float wk[K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      if (s0 + k < S) {
-        const float w = (1.0f - ex[k]) * (excl * pref[k]);
-        sd += w * zl[k];
-        sa += w;
+      for (int k = 0; k < K; ++k) {
+        wk[k] = (1.0f - ex[k]) * (excl * pref[k]);
+        if (s0 + k < S) {
+          sr += wk[k] * sigmoidf_(rw[k].x);
+          sg += wk[k] * sigmoidf_(rw[k].y);
+          sb += wk[k] * sigmoidf_(rw[k].z);
+          sa += wk[k];
+        } else {
+          wk[k] = 0.f;
+        }
       }
+      if (weights_out != nullptr) store_row<K>(weights_out, base, s0, S, vec, wk);
+      sr = group_sum<G>(sr); sg = group_sum<G>(sg); sb = group_sum<G>(sb); sa = group_sum<G>(sa);
+      const float bg = white_bkgd ? (1.0f - sa) : 0.0f;
+      const float er = sr + bg - target[ray * 3 + 0], eg = sg + bg - target[ray * 3 + 1],
+                  eb = sb + bg - target[ray * 3 + 2];
+      gr = 2.0f * er * loss_scale; gg = 2.0f * eg * loss_scale; gb = 2.0f * eb * loss_scale;
+      gd = 0.f; ga = 0.f; gdisp = 0.f;
+      if (lane == 0 && live) {
+        if (rgb_out != nullptr) { rgb_out[ray * 3 + 0] = sr + bg; rgb_out[ray * 3 + 1] = sg + bg; rgb_out[ray * 3 + 2] = sb + bg; }
+      }
+      // loss: one value per ray (lane 0 of each live group), summed over the warp, one atomic per warp pass
+      float lsum = (lane == 0 && live) ? (er * er + eg * eg + eb * eb) * loss_scale : 0.f;
+      lsum = warp_sum(lsum);
+      if ((threadIdx.x & 31) == 0) atomicAdd(loss, lsum);
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        if (s0 + k < S) {
+          const float w = (1.0f - ex[k]) * (excl * pref[k]);
+          sd += w * zl[k];
+          sa += w;
+        }
+      }
+      sd = group_sum<G>(sd); sa = group_sum<G>(sa);
+      gr = g_rgb ? g_rgb[ray * 3 + 0] : 0.f;
+      gg = g_rgb ? g_rgb[ray * 3 + 1] : 0.f;
+      gb = g_rgb ? g_rgb[ray * 3 + 2] : 0.f;
+      gd = g_depth ? g_depth[ray] : 0.f;
+      ga = g_acc ? g_acc[ray] : 0.f;
+      gdisp = g_disp ? g_disp[ray] : 0.f;
     }
-    sd = group_sum<G>(sd); sa = group_sum<G>(sa);
-    const float gr = g_rgb ? g_rgb[ray * 3 + 0] : 0.f;
-    const float gg = g_rgb ? g_rgb[ray * 3 + 1] : 0.f;
-    const float gb = g_rgb ? g_rgb[ray * 3 + 2] : 0.f;
-    float gd = g_depth ? g_depth[ray] : 0.f;
-    float ga = g_acc ? g_acc[ray] : 0.f;
-    const float gdisp = g_disp ? g_disp[ray] : 0.f;
     if (gdisp != 0.f) {  // disp = 1/max(1e-10, q), q = depth/acc
       const float q = sd / sa;
       if (q > 1e-10f) {
@@ -332,6 +372,16 @@ static inline int comp_grid(int64_t R, int S) {
   else if (S <= 384) KERNEL<12, 32><<<grid, block, 0, st>>>(__VA_ARGS__);                  \
   else KERNEL<16, 32><<<grid, block, 0, st>>>(__VA_ARGS__);
 
+#define CTX_COMP_DISPATCH_BWD(TRAIN, ...)                                                                   \
+  if (S <= 32) ctx::composite_bwd_kernel<4, 8, TRAIN><<<grid, block, 0, st>>>(__VA_ARGS__);                    \
+  else if (S <= 64) ctx::composite_bwd_kernel<4, 16, TRAIN><<<grid, block, 0, st>>>(__VA_ARGS__);              \
+  else if (S <= 96) ctx::composite_bwd_kernel<3, 32, TRAIN><<<grid, block, 0, st>>>(__VA_ARGS__);              \
+  else if (S <= 128) ctx::composite_bwd_kernel<4, 32, TRAIN><<<grid, block, 0, st>>>(__VA_ARGS__);             \
+  else if (S <= 192) ctx::composite_bwd_kernel<6, 32, TRAIN><<<grid, block, 0, st>>>(__VA_ARGS__);             \
+  else if (S <= 256) ctx::composite_bwd_kernel<8, 32, TRAIN><<<grid, block, 0, st>>>(__VA_ARGS__);             \
+  else if (S <= 384) ctx::composite_bwd_kernel<12, 32, TRAIN><<<grid, block, 0, st>>>(__VA_ARGS__);            \
+  else ctx::composite_bwd_kernel<16, 32, TRAIN><<<grid, block, 0, st>>>(__VA_ARGS__);
+
 extern "C" int ctx_composite_fwd(const float* raw, const float* z_vals, const float* rays_d,
                                  const float* noise, int64_t R, int S, int white_bkgd,
                                  float* rgb_map, float* disp_map, float* acc_map, float* weights,
@@ -362,7 +412,26 @@ extern "C" int ctx_composite_bwd(const float* raw, const float* z_vals, const fl
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ctx::comp_grid(R, S), block = ctx::kCompWarps * 32;
   const int vec = ctx::comp_vec(S, {z_vals, noise, g_weights});
-  CTX_COMP_DISPATCH(ctx::composite_bwd_kernel, (const float4*)raw, z_vals, rays_d, noise, R, S, vec,
-                    white_bkgd, g_rgb, g_disp, g_acc, g_weights, g_depth, (float4*)g_raw)
+  CTX_COMP_DISPATCH_BWD(false, (const float4*)raw, z_vals, rays_d, noise, R, S, vec, white_bkgd, g_rgb, g_disp,
+                        g_acc, g_weights, g_depth, (float4*)g_raw, nullptr, 0.f, nullptr, nullptr, nullptr)
+  CTX_RETURN_LAST();
+}
+
+// Fused training form of raw2outputs: forward + img2mse(rgb_map, target) + backward in one pass (see the kernel).
+// loss_scale = 1 / (3 R) for the mean over the rgb image; loss[0] is ADDED to (zero it once per step: the coarse and
+// the fine pass accumulate into the same scalar).  weights / rgb_map are optional outputs.
+extern "C" int ctx_composite_train(const float* raw, const float* z_vals, const float* rays_d, const float* noise,
+                                   int64_t R, int S, int white_bkgd, const float* target, float loss_scale,
+                                   float* loss, float* g_raw, float* weights, float* rgb_map, void* stream) {
+  if (R < 0 || S < 1 || S > 512) return CTX_ERR_BAD_ARG;
+  if (R == 0) return 0;
+  if (!raw || !z_vals || !rays_d || !target || !loss || !g_raw) return CTX_ERR_BAD_ARG;
+  if (reinterpret_cast<uintptr_t>(raw) % 16 != 0 || reinterpret_cast<uintptr_t>(g_raw) % 16 != 0)
+    return CTX_ERR_BAD_ARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int grid = ctx::comp_grid(R, S), block = ctx::kCompWarps * 32;
+  const int vec = ctx::comp_vec(S, {z_vals, noise, weights});
+  CTX_COMP_DISPATCH_BWD(true, (const float4*)raw, z_vals, rays_d, noise, R, S, vec, white_bkgd, nullptr, nullptr,
+                        nullptr, nullptr, nullptr, (float4*)g_raw, target, loss_scale, loss, weights, rgb_map)
   CTX_RETURN_LAST();
 }

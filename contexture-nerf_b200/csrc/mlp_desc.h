@@ -34,13 +34,16 @@ typedef struct {
   int32_t bias_off;  /* float offset into fparams */
   int32_t w_off;     /* byte offset of this layer's first chunk in the packed stream */
   int32_t wt_off;    /* byte offset in the transposed (dgrad) stream, -1 if none */
-  int32_t act_slot;  /* byte offset, within a tile's activation record, of this layer's OUTPUT */
+  int32_t act_slot;  /* byte offset, within a tile's activation record, of this layer's OUTPUT; -1: the layer keeps no
+                        record (feature_linear: its weight gradients are rebuilt algebraically, see mlp_wgrad.cu) */
   int32_t in_slot;   /* byte offset of the record holding this layer's h INPUT (-1: none) */
   int32_t mask_slot; /* byte offset of the ReLU sign-bit record (128 rows x N/32 words), -1: none */
   int32_t bias_mma;  /* 2-CTA kernels fold the bias into the GEMM through the constant-1 pad channel of the x
                         buffer: 0 = it rides in an x chunk this layer reads anyway, 1 = one extra K=16 MMA whose
                         B operand is the 16-wide "bias chunk" stored after the layer's regular chunks */
   int32_t bias_a_off;/* byte offset inside the x tile of the 16 channels ending in the constant-1 channel */
+  int32_t rec_ch;    /* channel width of the record slot (>= N: the views layer's slot also holds the 16 g_out channels,
+                        so that [dZ_views | g_out] is ONE 144-wide wgrad operand) */
 } CtxMlpLayer;
 
 typedef struct {
@@ -54,6 +57,8 @@ typedef struct {
   int32_t n_fparams;     /* floats in fparams */
   int32_t act_tile_bytes;/* bytes of one 128-point activation record */
   int32_t xp_slot, xd_slot, gout_slot;
+  int32_t gout_ch0;      /* first channel of the 16 g_out channels inside the slot at gout_slot */
+  int32_t gout_rec_ch;   /* channel width of that slot (16, or 144 when it is the views layer's) */
   CtxMlpLayer L[CTX_MLP_MAX_LAYERS];
 } CtxMlpNet;
 

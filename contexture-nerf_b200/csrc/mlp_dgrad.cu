@@ -171,6 +171,7 @@ mlp_dgrad_kernel(const __grid_constant__ DgradArgs a) {
     const int out_ch = net.out_ch, act_tile_bytes = net.act_tile_bytes, gout_slot = net.gout_slot;
     const int last = net.n_layers - 1;
     const int lastN = net.L[last].N, last_mask = net.L[last].mask_slot, last_act = net.L[last].act_slot;
+    const int last_rec = net.L[last].rec_ch, gout_ch0 = net.gout_ch0, gout_rec = net.gout_rec_ch;
     const int64_t nP = a.P;
     uint32_t acc_phase[2] = {0, 0};
 
@@ -205,8 +206,8 @@ mlp_dgrad_kernel(const __grid_constant__ DgradArgs a) {
         float gv[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) gv[i] = i < 4 ? g[i] : 0.f;
-        store_row8(nullptr, row, 0, gv, false, drec + gout_slot, 16);
-        store_row8(nullptr, row, 8, gv + 8, false, drec + gout_slot, 16);
+        store_row8(nullptr, row, gout_ch0, gv, false, drec + gout_slot, gout_rec);
+        store_row8(nullptr, row, gout_ch0 + 8, gv + 8, false, drec + gout_slot, gout_rec);
       }
       const int nw = lastN / 32;
       const uint32_t* mrow = reinterpret_cast<const uint32_t*>(rec + last_mask) + row;   // [column block][row]
@@ -230,7 +231,7 @@ mlp_dgrad_kernel(const __grid_constant__ DgradArgs a) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = ((neg >> (31 - j)) & 1u) ? 0.f : v[j];
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) store_row8(my_h, row, cb * 32 + j, v + j, false, drec + last_act, lastN);
+        for (int j = 0; j < 32; j += 8) store_row8(my_h, row, cb * 32 + j, v + j, false, drec + last_act, last_rec);
       }
     };
 
@@ -279,7 +280,7 @@ mlp_dgrad_kernel(const __grid_constant__ DgradArgs a) {
               }
 #pragma unroll
               for (int j = 0; j < 32; j += 8)
-                store_row8(NEXT ? my_h : nullptr, row, cb * 32 + j, v + j, false, drec + Dact, 256);
+                store_row8(NEXT ? my_h : nullptr, row, cb * 32 + j, v + j, false, Dact >= 0 ? drec + Dact : nullptr, 256);
             };
             uint32_t va[32];
 #pragma unroll

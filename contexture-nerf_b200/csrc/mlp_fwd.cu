@@ -340,7 +340,7 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
     for (int64_t it = cid; it < n_citers; it += ncl) {
       for (int l = 0; l < net.n_layers; ++l) {
         const int Lepi = net.L[l].epi, LN = net.L[l].N, Lrelu = net.L[l].relu;
-        const int Lmask = net.L[l].mask_slot, Lact = net.L[l].act_slot;
+        const int Lmask = net.L[l].mask_slot, Lact = net.L[l].act_slot, Lrec = net.L[l].rec_ch;
         const bool is_final = (Lepi == CTX_EPI_FINAL_VIEWS || Lepi == CTX_EPI_FINAL_OUT);
         const int ncb = LN / 64;            // 32-column blocks handled by this warp (its half of N)
 #pragma unroll
@@ -367,7 +367,7 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
             constexpr int EPI = decltype(epi_c)::value;
             constexpr bool RELU = decltype(relu_c)::value;
             constexpr bool FINAL = (EPI == CTX_EPI_FINAL_VIEWS || EPI == CTX_EPI_FINAL_OUT);
-            uint8_t* const grec = kRec ? rec + Lact : nullptr;
+            uint8_t* const grec = (kRec && Lact >= 0) ? rec + Lact : nullptr;   // (feature layer: no record)
             auto process = [&](const uint32_t (&vr)[32], int cb) {
               if constexpr (kRec && RELU) {
                 // bit (31-j) = sign of pre-activation j (the ReLU mask the dgrad kernel reads); four independent
@@ -411,7 +411,7 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
               if constexpr (!FINAL || kRec) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 8)
-                  store_row8(FINAL ? nullptr : my_h, row, cb * 32 + j, v + j, RELU, grec, LN);
+                  store_row8(FINAL ? nullptr : my_h, row, cb * 32 + j, v + j, RELU, grec, Lrec);
               }
             };
             uint32_t va[32];
@@ -519,10 +519,10 @@ extern "C" int ctx_mlp_set_hang_buffer(void* p) { ctx_mlp_hang_buffer = p; retur
 extern "C" int ctx_mlp_set_debug(int f) { ctx_mlp_debug_flags = f; return 0; }
 extern "C" int ctx_mlp_set_prof_buffer(void* p) { ctx_mlp_prof_buffer = p; return 0; }
 
-extern "C" int ctx_mlp_fwd(const void* net_host, const void* wpacked, const float* fparams, int mode,
-                            const float* x, int x_ld, const float* rays_o, const float* rays_d,
-                            const float* viewdirs, const float* z, int S, int L_pts, int L_dirs, int64_t P,
-                            float* out, void* acts, void* stream) {
+extern "C" int ctx_mlp_fwd_ex(const void* net_host, const void* wpacked, const float* fparams, int mode,
+                               const float* x, int x_ld, const float* rays_o, const float* rays_d,
+                               const float* viewdirs, const float* z, int S, int L_pts, int L_dirs, int64_t P,
+                               float* out, void* acts, int max_sms, void* stream) {
   if (P < 0) return CTX_ERR_BAD_ARG;
   if (P == 0) return 0;                       // empty batch: nothing to launch (its pointers may be null)
   if (!net_host || !wpacked || !fparams || !out) return CTX_ERR_BAD_ARG;
@@ -559,7 +559,18 @@ extern "C" int ctx_mlp_fwd(const void* net_host, const void* wpacked, const floa
   cudaError_t e = cudaMemsetAsync(out, 0, (size_t)P * a.net.out_ch * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
   const int64_t citers = ctx::ceil_div(P, (int64_t)ctx::kTileM * 4);
-  const int ncl = (int)(citers < ctx::num_sms() / 2 ? citers : ctx::num_sms() / 2);
+  int cap = ctx::num_sms() / 2;   // one cluster per SM pair; a smaller SM budget leaves room for a concurrent kernel
+  if (max_sms > 0 && max_sms / 2 < cap) cap = max_sms / 2;
+  if (cap < 1) cap = 1;
+  const int ncl = (int)(citers < cap ? citers : cap);
   kernels[(a.prof ? 2 : 0) + (a.acts ? 1 : 0)]<<<2 * ncl, ctx::kMlpThreads, ctx::kMlp2SmemBytes, st>>>(a);
   CTX_RETURN_LAST();
+}
+
+extern "C" int ctx_mlp_fwd(const void* net_host, const void* wpacked, const float* fparams, int mode,
+                            const float* x, int x_ld, const float* rays_o, const float* rays_d,
+                            const float* viewdirs, const float* z, int S, int L_pts, int L_dirs, int64_t P,
+                            float* out, void* acts, void* stream) {
+  return ctx_mlp_fwd_ex(net_host, wpacked, fparams, mode, x, x_ld, rays_o, rays_d, viewdirs, z, S, L_pts, L_dirs, P,
+                        out, acts, 0, stream);
 }

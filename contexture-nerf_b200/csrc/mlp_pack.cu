@@ -124,7 +124,7 @@ extern "C" int ctx_mlp_describe(int D, uint32_t skip_mask, int in_pts, int in_vi
   int w_off = 0, wt_off = 0, f_off = 0, slot = 0;
   net.xp_slot = slot; slot += 128 * CTX_MLP_XP_PAD * 2;
   net.xd_slot = slot; slot += 128 * CTX_MLP_XD_PAD * 2;
-  net.gout_slot = slot; slot += 128 * 16 * 2;
+  if (in_views == 0) { net.gout_slot = slot; slot += 128 * 16 * 2; net.gout_ch0 = 0; net.gout_rec_ch = 16; }
   int n = 0, prev_slot = -1;
   for (int l = 0; l < D; ++l, ++n) {
     CtxMlpLayer& L = net.L[n];
@@ -137,7 +137,7 @@ extern "C" int ctx_mlp_describe(int D, uint32_t skip_mask, int in_pts, int in_vi
     L.bias_mma = L.n_x_pre ? 0 : 1; L.bias_a_off = (CTX_MLP_XP_PAD - 16) / 8 * 128 * 16;
     if (L.bias_mma) w_off += 16 * L.N * 2;
     if (l > 0) { L.wt_off = wt_off; wt_off += CTX_MLP_W * 256 * 2; } else L.wt_off = -1;
-    L.act_slot = slot; slot += 128 * L.N * 2;
+    L.act_slot = slot; slot += 128 * L.N * 2; L.rec_ch = L.N;
     L.mask_slot = slot; slot += 128 * (L.N / 32) * 4;
     L.in_slot = prev_slot; prev_slot = L.act_slot;
   }
@@ -149,9 +149,11 @@ extern "C" int ctx_mlp_describe(int D, uint32_t skip_mask, int in_pts, int in_vi
     F.w_off = w_off; w_off += F.n_h * CTX_MLP_KC * F.N * 2;
     F.bias_mma = 1; F.bias_a_off = (CTX_MLP_XD_PAD - 16) / 8 * 128 * 16; w_off += 16 * F.N * 2;
     F.wt_off = wt_off; wt_off += CTX_MLP_W * 256 * 2;
-    F.act_slot = slot; slot += 128 * F.N * 2;
+    // no record of the feature layer: it is linear, so dW_feature, dW_views[:, :256] and their biases follow from
+    // G = dZ_views^T h_{D-1} (one wgrad job) and the weights themselves (mlp_wgrad.cu, wgrad_post_kernel)
+    F.act_slot = -1; F.rec_ch = F.N;
     F.mask_slot = -1;
-    F.in_slot = prev_slot; prev_slot = F.act_slot;
+    F.in_slot = prev_slot; prev_slot = -1;
     ++n;
     CtxMlpLayer& V = net.L[n];  // views_linears.0: [feature | dirs] -> 128, relu ; rgb head folded in
     V.n_x_pre = 0; V.n_h = h_chunks; V.n_x_post = CTX_MLP_XD_PAD / CTX_MLP_KC; V.N = CTX_MLP_W / 2; V.relu = 1;
@@ -160,7 +162,9 @@ extern "C" int ctx_mlp_describe(int D, uint32_t skip_mask, int in_pts, int in_vi
     V.w_off = w_off; w_off += (V.n_h + V.n_x_post) * CTX_MLP_KC * V.N * 2;
     V.bias_mma = 0; V.bias_a_off = 0;
     V.wt_off = wt_off; wt_off += (CTX_MLP_W / 2) * 256 * 2;
-    V.act_slot = slot; slot += 128 * V.N * 2;
+    V.rec_ch = V.N + 16;   // [v or dZ_views (128) | g_out (16)]
+    V.act_slot = slot; slot += 128 * V.rec_ch * 2;
+    net.gout_slot = V.act_slot; net.gout_ch0 = V.N; net.gout_rec_ch = V.rec_ch;
     V.mask_slot = slot; slot += 128 * (V.N / 32) * 4;
     V.in_slot = prev_slot;
     ++n;

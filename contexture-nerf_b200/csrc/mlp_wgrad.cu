@@ -35,6 +35,8 @@ constexpr size_t kWgSmemBytes = (size_t)kWgUnits * kWgUnitBytes + 256;
 struct WgJob {
   int a_slot, a_ch, a_dz;       // A operand tile: record offset, channels (M, multiple of 128), from dZ records?
   int b_slot, b_ch, b_dz;       // B operand tile: channels = N (multiple of 16)
+  int a_hstride, b_hstride;     // bytes between the two 64-point halves of the slot (= slot width x 128; a job may
+                                // read a channel sub-range of a wider slot: any 8-aligned range of a half is contiguous)
   float* out; int ld_out; int col_off;
   int transposed;               // 1: out[(n-n_lo)*ld + col_off + m]   0: out[m*ld + col_off + (n-n_lo)]
   int m_valid, n_lo, n_hi;
@@ -94,7 +96,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const __grid_c
         const int s = u % kWgUnits;
         tc::mbar_wait(&ctl->empty[s], ((u / kWgUnits) & 1) ^ 1);
         if (tc::elect_one()) {
-          const uint8_t* src = which == 0 ? a_src + base + (size_t)hf * a_bytes : b_src + base + (size_t)hf * b_bytes;
+          const uint8_t* src = which == 0 ? a_src + base + (size_t)hf * J.a_hstride : b_src + base + (size_t)hf * J.b_hstride;
           const uint32_t bytes = which == 0 ? a_bytes : b_bytes;
           tc::mbar_arrive_expect_tx(&ctl->full[s], bytes);
           tc::bulk_g2s(smem + s * kWgUnitBytes, src, bytes, &ctl->full[s]);
@@ -228,14 +230,76 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const __grid_c
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// View-direction head without a feature-layer record.  feature = W_f h + b_f is linear (no activation,
+// reference comment block src/run_nerf_helpers.py:119-121), v = relu(W_vh feature + W_vd x_d + b_v).  With
+//     G[h-channel m][n] = sum_points [dZ_v | g_out][point, n] * h[point, m]      (ONE wgrad job, N = 144)
+//     s[n]              = sum_points [dZ_v | g_out][point, n]                     (its column sums)
+// the gradients of feature_linear, of the feature columns of views_linears.0 and of alpha_linear follow exactly:
+//     dW_f  = W_vh^T G_v          db_f = W_vh^T s_v
+//     dW_vh = G_v W_f^T + s_v b_f^T        db_v = s_v
+//     dw_alpha = G[:, 128+3]      db_alpha = s[128+3]
+// (W_vh, W_f, b_f as the kernels see them: rounded to bf16).  So neither the feature activations nor dZ_feature are
+// ever written to HBM, and the two 1 KB-per-point jobs that read them are replaced by one 800 B-per-point job.
+// scratch: Gt [144][256] (n-major) followed by s [144], fp32, zeroed by the launcher.
+constexpr int kPostGtFloats = 144 * 256, kPostScratchFloats = 144 * 256 + 144;
+__device__ __forceinline__ float bf16r(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+
+__global__ void wgrad_post_kernel(const float* __restrict__ scratch, const float* __restrict__ W_f,
+                                  const float* __restrict__ b_f, const float* __restrict__ W_v, int ld_v,
+                                  float* __restrict__ gW_f, float* __restrict__ gb_f, float* __restrict__ gW_v,
+                                  float* __restrict__ gb_v, float* __restrict__ gw_alpha, float* __restrict__ gb_alpha) {
+  const float* Gt = scratch;
+  const float* sv = scratch + kPostGtFloats;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < 256 * 256) {                       // dW_f[f][m] += sum_v W_vh[v][f] Gt[v][m]
+    const int f = t >> 8, m = t & 255;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int v = 0; v < 128; ++v) acc = fmaf(bf16r(__ldg(W_v + v * ld_v + f)), Gt[v * 256 + m], acc);
+    gW_f[t] += acc;
+    if (m == 0) {
+      float b = 0.f;
+      for (int v = 0; v < 128; ++v) b = fmaf(bf16r(__ldg(W_v + v * ld_v + f)), sv[v], b);
+      gb_f[f] += b;
+    }
+    return;
+  }
+  const int u = t - 256 * 256;
+  if (u < 128 * 256) {                       // dW_vh[v][f] += sum_m Gt[v][m] W_f[f][m] + s_v[v] b_f[f]
+    const int v = u >> 8, f = u & 255;
+    float acc = sv[v] * bf16r(b_f[f]);
+    const float4* wrow = reinterpret_cast<const float4*>(W_f + f * 256);
+    const float4* grow = reinterpret_cast<const float4*>(Gt + v * 256);
+#pragma unroll 4
+    for (int m4 = 0; m4 < 64; ++m4) {
+      const float4 w = __ldg(wrow + m4), g = grow[m4];
+      acc = fmaf(g.x, bf16r(w.x), acc); acc = fmaf(g.y, bf16r(w.y), acc);
+      acc = fmaf(g.z, bf16r(w.z), acc); acc = fmaf(g.w, bf16r(w.w), acc);
+    }
+    gW_v[v * ld_v + f] += acc;
+    if (f == 0) gb_v[v] += sv[v];
+    return;
+  }
+  const int a = u - 128 * 256;
+  if (a < 256) gw_alpha[a] += Gt[(128 + 3) * 256 + a];
+  if (a == 0) gb_alpha[0] += sv[128 + 3];
+}
+
 }  // namespace ctx
 
 // grads: HOST array of DEVICE pointers in the order of ctx_mlp_pack's `params`
 // (gradients are ACCUMULATED into them: zero them first for a fresh gradient).
+// params: the fp32 parameters themselves, same order (the view-direction head rebuilds the gradients of
+// feature_linear / views_linears.0[:, :256] from G and the weights, see wgrad_post_kernel); scratch: device buffer of
+// ctx_mlp_wgrad_scratch_floats() floats (both only used with a view-direction net; may be null otherwise).
 // max_sms > 0: use at most that many CTAs (rounded down to even) and launch them as 2-CTA clusters, so that they
 // pack into whole SM pairs and a concurrent cluster kernel (dgrad of the other network) finds free pairs.
+extern "C" int ctx_mlp_wgrad_scratch_floats(void) { return ctx::kPostScratchFloats; }
+
 extern "C" int ctx_mlp_wgrad_ex(const void* net_host, const void* acts, const void* dacts, int64_t P,
-                                float* const* grads, int n_grads, int max_sms, void* stream) {
+                                float* const* grads, int n_grads, const float* const* params, float* scratch,
+                                int max_sms, void* stream) {
   if (P < 0) return CTX_ERR_BAD_ARG;
   if (P == 0) return 0;
   if (!net_host || !acts || !dacts || !grads) return CTX_ERR_BAD_ARG;
@@ -243,11 +307,16 @@ extern "C" int ctx_mlp_wgrad_ex(const void* net_host, const void* acts, const vo
   const bool views = net.in_views > 0;
   const int D = views ? net.n_layers - 2 : net.n_layers;
   if (n_grads != 2 * D + (views ? 8 : 2)) return CTX_ERR_BAD_ARG;
+  if (views && (!params || !scratch)) return CTX_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   static ctx::DeviceOnce attr_once;
   if (attr_once.needed()) {
     cudaError_t e = cudaFuncSetAttribute(ctx::mlp_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)ctx::kWgSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (views) {
+    cudaError_t e = cudaMemsetAsync(scratch, 0, sizeof(float) * ctx::kPostScratchFloats, st);
     if (e != cudaSuccess) return (int)e;
   }
   // ---------------- wgrad ----------------
@@ -259,19 +328,27 @@ extern "C" int ctx_mlp_wgrad_ex(const void* net_host, const void* acts, const vo
     w.n_tiles = n_tiles;
     int nj = 0;
     float cost[ctx::kWgMaxJobs];
-    auto add = [&](int a_slot, int a_ch, int a_dz, int b_slot, int b_ch, int b_dz, float* out, int ld, int col_off,
-                   int transposed, int m_valid, int n_lo, int n_hi, float* bias, int bias_from_b, int blo, int bhi) {
+    // operand = (slot byte offset, slot channel width, first channel, channels)
+    struct Opnd { int slot, rec_ch, ch0, ch, dz; };
+    auto add = [&](Opnd A, Opnd B, float* out, int ld, int col_off, int transposed, int m_valid, int n_lo, int n_hi,
+                   float* bias, int bias_from_b, int blo, int bhi) {
       ctx::WgJob& J = w.job[nj];
-      J.a_slot = a_slot; J.a_ch = a_ch; J.a_dz = a_dz; J.b_slot = b_slot; J.b_ch = b_ch; J.b_dz = b_dz;
+      J.a_slot = A.slot + (A.ch0 >> 3) * 1024; J.a_ch = A.ch; J.a_dz = A.dz; J.a_hstride = A.rec_ch * 128;
+      J.b_slot = B.slot + (B.ch0 >> 3) * 1024; J.b_ch = B.ch; J.b_dz = B.dz; J.b_hstride = B.rec_ch * 128;
       J.out = out; J.ld_out = ld; J.col_off = col_off; J.transposed = transposed; J.m_valid = m_valid;
       J.n_lo = n_lo; J.n_hi = n_hi; J.bias_out = bias; J.bias_from_b = bias_from_b; J.bias_lo = blo; J.bias_hi = bhi;
-      cost[nj] = (float)(a_ch + b_ch);   // HBM bytes per point decide the split, the kernel is bandwidth-bound
+      cost[nj] = (float)(A.ch + B.ch);   // HBM bytes per point decide the split, the kernel is bandwidth-bound
       ++nj;
     };
+    const Opnd XP = {net.xp_slot, CTX_MLP_XP_PAD, 0, CTX_MLP_XP_PAD, 0};
+    const Opnd XD = {net.xd_slot, CTX_MLP_XD_PAD, 0, CTX_MLP_XD_PAD, 0};
+    const Opnd GOUT = {net.gout_slot, net.gout_rec_ch, net.gout_ch0, 16, 1};
     for (int l = 0; l < net.n_layers; ++l) {
       const CtxMlpLayer& L = net.L[l];
+      if (views && l == D) continue;   // feature_linear: rebuilt from G (below)
+      const bool is_views_layer = views && l == D + 1;
       int pi;
-      if (l < D) pi = 2 * l; else if (l == D) pi = 2 * D; else pi = 2 * D + 4;
+      if (l < D) pi = 2 * l; else pi = 2 * D + 4;
       float* gW = grads[pi];
       float* gb = grads[pi + 1];
       int ld = 0;
@@ -280,36 +357,39 @@ extern "C" int ctx_mlp_wgrad_ex(const void* net_host, const void* acts, const vo
       if (L.n_h) ld += 256;
       const int xd_col = ld;
       if (L.n_x_post) ld += net.in_views;
+      const Opnd DZ = {L.act_slot, L.rec_ch, 0, L.N, 1};
       bool bias_done = false;
-      if (L.n_h) {  // h segment: transposed job, A = input activations (M = in), B = dZ (N = out)
-        add(L.in_slot, 256, 0, L.act_slot, L.N, 1, gW, ld, h_col, 1, 256, 0, L.N, gb, 1, 0, L.N);
+      if (L.n_h && !is_views_layer) {  // h segment: transposed job, A = input activations (M = in), B = dZ (N = out)
+        add({L.in_slot, 256, 0, 256, 0}, DZ, gW, ld, h_col, 1, 256, 0, L.N, gb, 1, 0, L.N);
         bias_done = true;
       }
       if (L.n_x_pre) {  // point-encoding segment: A = dZ (M = out), B = x_p tile (N = 64, 63 real)
-        add(L.act_slot, L.N, 1, net.xp_slot, CTX_MLP_XP_PAD, 0, gW, ld, 0, 0, L.N, 0, net.in_pts,
-            bias_done ? nullptr : gb, 0, 0, L.N);
+        add(DZ, XP, gW, ld, 0, 0, L.N, 0, net.in_pts, bias_done ? nullptr : gb, 0, 0, L.N);
         bias_done = true;
       }
-      if (L.n_x_post) {  // view-encoding segment
-        add(L.act_slot, L.N, 1, net.xd_slot, CTX_MLP_XD_PAD, 0, gW, ld, xd_col, 0, L.N, 0, net.in_views, nullptr, 0,
-            0, 0);
+      if (L.n_x_post) {  // view-encoding segment (its bias comes out of the G job's column sums)
+        add(DZ, XD, gW, ld, xd_col, 0, L.N, 0, net.in_views, nullptr, 0, 0, 0);
       }
     }
     if (views) {
-      const CtxMlpLayer& H = net.L[D - 1];           // alpha_linear reads h_{D-1}
+      const CtxMlpLayer& H = net.L[D - 1];           // h_{D-1}: input of feature_linear and alpha_linear
       const CtxMlpLayer& V = net.L[net.n_layers - 1];
-      add(H.act_slot, 256, 0, net.gout_slot, 16, 1, grads[2 * D + 2], 256, 0, 1, 256, 3, 4, grads[2 * D + 3], 1, 3, 4);
-      add(V.act_slot, 128, 0, net.gout_slot, 16, 1, grads[2 * D + 6], 128, 0, 1, 128, 0, 3, grads[2 * D + 7], 1, 0, 3);
+      // G job: A = h_{D-1} (M = 256), B = [dZ_views | g_out] (N = 144) -> Gt [144][256] and the column sums s [144]
+      add({H.act_slot, 256, 0, 256, 0}, {V.act_slot, V.rec_ch, 0, V.rec_ch, 1}, scratch, 256, 0, 1, 256, 0, V.rec_ch,
+          scratch + ctx::kPostGtFloats, 1, 0, V.rec_ch);
+      // rgb_linear: A = v (M = 128), B = g_out (N = 16, channels 0..2 are g_rgb)
+      add({V.act_slot, V.rec_ch, 0, 128, 0}, GOUT, grads[2 * D + 6], 128, 0, 1, 128, 0, 3, grads[2 * D + 7], 1, 0, 3);
     } else {
       const CtxMlpLayer& H = net.L[D - 1];
-      add(H.act_slot, 256, 0, net.gout_slot, 16, 1, grads[2 * D], 256, 0, 1, 256, 0, net.out_ch, grads[2 * D + 1], 1,
+      add({H.act_slot, 256, 0, 256, 0}, GOUT, grads[2 * D], 256, 0, 1, 256, 0, net.out_ch, grads[2 * D + 1], 1,
           0, net.out_ch);
     }
-    // distribute the 148 CTAs over the jobs proportionally to their HBM traffic
+    // distribute the CTAs over the jobs proportionally to their HBM traffic
     float total = 0.f;
     for (int j = 0; j < nj; ++j) total += cost[j];
     int budget = ctx::num_sms(), begin = 0;
-    const bool capped = max_sms > 0 && max_sms < ctx::num_sms();
+    if (budget > ctx::kNumSMs) budget = ctx::kNumSMs;
+    const bool capped = max_sms > 0 && max_sms < budget;
     if (capped) budget = max_sms & ~1;
     if (budget < 2 * nj) return CTX_ERR_UNSUPPORTED;
     int given[ctx::kWgMaxJobs];
@@ -340,12 +420,25 @@ extern "C" int ctx_mlp_wgrad_ex(const void* net_host, const void* acts, const vo
       ctx::mlp_wgrad_kernel<<<begin, ctx::kWgThreads, ctx::kWgSmemBytes, st>>>(w);
     }
   }
+  {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (views) {
+    const int n_out = 256 * 256 + 128 * 256 + 256;
+    const int ld_v = 256 + net.in_views;
+    ctx::wgrad_post_kernel<<<(n_out + 255) / 256, 256, 0, st>>>(scratch, params[2 * D], params[2 * D + 1],
+                                                                params[2 * D + 4], ld_v, grads[2 * D], grads[2 * D + 1],
+                                                                grads[2 * D + 4], grads[2 * D + 5], grads[2 * D + 2],
+                                                                grads[2 * D + 3]);
+  }
   CTX_RETURN_LAST();
 }
 
 extern "C" int ctx_mlp_wgrad(const void* net_host, const void* acts, const void* dacts, int64_t P,
-                             float* const* grads, int n_grads, void* stream) {
-  return ctx_mlp_wgrad_ex(net_host, acts, dacts, P, grads, n_grads, 0, stream);
+                             float* const* grads, int n_grads, const float* const* params, float* scratch,
+                             void* stream) {
+  return ctx_mlp_wgrad_ex(net_host, acts, dacts, P, grads, n_grads, params, scratch, 0, stream);
 }
 
 extern "C" int ctx_mlp_dgrad_ex(const void* net_host, const void* wtpacked, const float* fparams, const float* g_out,
@@ -364,8 +457,8 @@ extern "C" int ctx_mlp_dgrad(const void* net_host, const void* wtpacked, const f
 
 extern "C" int ctx_mlp_bwd(const void* net_host, const void* wtpacked, const float* fparams,
                            const float* g_out, const void* acts, void* dacts, int64_t P, float* const* grads,
-                           int n_grads, void* stream) {
+                           int n_grads, const float* const* params, float* scratch, void* stream) {
   const int rc = ctx_mlp_dgrad(net_host, wtpacked, fparams, g_out, acts, dacts, P, stream);
   if (rc != 0) return rc;
-  return ctx_mlp_wgrad(net_host, acts, dacts, P, grads, n_grads, stream);
+  return ctx_mlp_wgrad(net_host, acts, dacts, P, grads, n_grads, params, scratch, stream);
 }

@@ -21,6 +21,35 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// Device-side step state of the captured training step: ctr[0] = Philox seed offset (raygen / resample add it to their
+// seed), ctr[1] = Adam step count.  The tick runs first in every step: it advances both and zeroes the loss scalar
+// the fused compositing kernels accumulate into, so a CUDA-graph replay needs no host-side argument to change.
+__global__ void step_tick_kernel(unsigned long long* __restrict__ ctr, float* __restrict__ loss) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    ctr[0] += 2ull;
+    ctr[1] += 1ull;
+    if (loss) loss[0] = 0.f;
+  }
+}
+
+// Adam with the step count read from the device counter (bias corrections formed per thread: two powf)
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, int64_t n, float lr, float b1, float b2, float eps,
+                                const unsigned long long* __restrict__ ctr, float wd, float grad_scale) {
+  const float step = (float)ctr[1];
+  const float bc1 = 1.f - powf(b1, step);
+  const float bc2_sqrt = sqrtf(1.f - powf(b2, step));
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * grad_scale;
+    if (wd != 0.f) gi += wd * p[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
 // loss = mean((a-t)^2) [+ mean((b-t)^2)]; g_a = 2(a-t)/n * scale, g_b likewise.  One CTA.
 __global__ void mse_pair_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                 const float* __restrict__ t, int64_t n, float scale, float* __restrict__ loss,
@@ -99,6 +128,25 @@ extern "C" int ctx_adam_step(float* params, const float* grads, float* exp_avg, 
   if (blocks > ctx::num_sms() * 8) blocks = ctx::num_sms() * 8;
   ctx::adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1,
                                                                   beta2, eps, bc1, bc2, weight_decay, grad_scale);
+  CTX_RETURN_LAST();
+}
+
+extern "C" int ctx_step_tick(void* counters, float* loss, void* stream) {
+  if (!counters) return CTX_ERR_BAD_ARG;
+  ctx::step_tick_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned long long*)counters, loss);
+  CTX_RETURN_LAST();
+}
+
+extern "C" int ctx_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                 float lr, float beta1, float beta2, float eps, const void* counters,
+                                 float weight_decay, float grad_scale, void* stream) {
+  if (n < 0 || !params || !grads || !exp_avg || !exp_avg_sq || !counters) return CTX_ERR_BAD_ARG;
+  if (n == 0) return 0;
+  int64_t blocks = ctx::ceil_div(n, 256);
+  if (blocks > ctx::num_sms() * 8) blocks = ctx::num_sms() * 8;
+  ctx::adam_dev_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1,
+                                                                      beta2, eps, (const unsigned long long*)counters,
+                                                                      weight_decay, grad_scale);
   CTX_RETURN_LAST();
 }
 

@@ -30,6 +30,7 @@ struct RaygenParams {
   int perturb;            // 0: none, 1: jitter
   const float* jitter;    // optional uniforms [n_rays, n_samples]; else Philox(seed)
   uint64_t seed;
+  const uint64_t* seed_dev;   // optional device counter ADDED to seed (a captured CUDA graph replays with fresh numbers)
   // optional bounding sphere: per-ray near/far = sphere entry/exit (cfg 4)
   int use_sphere;
   float sph_cx, sph_cy, sph_cz, sph_r;
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(kRayWarps * 32) raygen_kernel(RaygenParams p) 
     for (int j = 0; j < 3; ++j) rot[k][j] = __ldg(p.c2w + k * p.c2w_ld + j);
     org[k] = __ldg(p.c2w + k * p.c2w_ld + 3);
   }
+  const uint64_t seed = p.seed + (p.seed_dev ? *p.seed_dev : 0ull);
   for (int64_t r = warp0; r < p.n_rays; r += nwarps) {
     const int64_t pix = p.ray_idx ? p.ray_idx[r] : r;
     const uint32_t pix32 = (uint32_t)pix;                       // H*W < 2^31 is checked by the launcher
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(kRayWarps * 32) raygen_kernel(RaygenParams p) 
     if (p.near_far && lane < 2) p.near_far[r * 2 + lane] = lane == 0 ? near : far;
     if (p.z_vals)
       write_z_row(p.z_vals + r * p.n_samples, near, far, p.n_samples, p.lindisp, p.perturb,
-                  p.jitter ? p.jitter + r * p.n_samples : nullptr, p.seed, (uint64_t)r, lane, nl);
+                  p.jitter ? p.jitter + r * p.n_samples : nullptr, seed, (uint64_t)r, lane, nl);
   }
 }
 
@@ -266,7 +268,7 @@ extern "C" int ctx_raygen_fwd(int H, int W, float fx, float fy, float cx, float 
                               int c2w_ld, const int64_t* ray_idx, int64_t n_rays, int use_ndc,
                               float ndc_focal, float ndc_near, int n_samples, float near, float far,
                               int lindisp, int perturb, const float* jitter, uint64_t seed,
-                              int use_sphere, const float* sphere /*host: cx,cy,cz,r*/,
+                              const uint64_t* seed_dev, int use_sphere, const float* sphere /*host: cx,cy,cz,r*/,
                               float* rays_o, float* rays_d, float* viewdirs, float* z_vals,
                               float* near_far, void* stream) {
   if (H < 1 || W < 1 || n_rays < 0 || !c2w || c2w_ld < 4 || n_samples < 0) return CTX_ERR_BAD_ARG;
@@ -278,7 +280,7 @@ extern "C" int ctx_raygen_fwd(int H, int W, float fx, float fy, float cx, float 
   p.H = H; p.W = W; p.fx = fx; p.fy = fy; p.cx = cx; p.cy = cy; p.c2w = c2w; p.c2w_ld = c2w_ld;
   p.ray_idx = ray_idx; p.n_rays = n_rays; p.use_ndc = use_ndc; p.ndc_focal = ndc_focal;
   p.ndc_near = ndc_near; p.n_samples = n_samples; p.near = near; p.far = far; p.lindisp = lindisp;
-  p.perturb = perturb; p.jitter = jitter; p.seed = seed; p.use_sphere = use_sphere;
+  p.perturb = perturb; p.jitter = jitter; p.seed = seed; p.seed_dev = seed_dev; p.use_sphere = use_sphere;
   p.sph_cx = use_sphere ? sphere[0] : 0.f; p.sph_cy = use_sphere ? sphere[1] : 0.f;
   p.sph_cz = use_sphere ? sphere[2] : 0.f; p.sph_r = use_sphere ? sphere[3] : 0.f;
   p.rays_o = rays_o; p.rays_d = rays_d; p.viewdirs = viewdirs;

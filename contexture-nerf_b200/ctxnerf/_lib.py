@@ -25,13 +25,13 @@ _SIGNATURES = {
     "ctx_posenc_bwd": (c_int, [P, P, P, c_int64, c_int, c_int, c_int, c_int, P]),
     "ctx_raygen_fwd": (c_int, [c_int, c_int, c_float, c_float, c_float, c_float, P, c_int, P, c_int64,
                                c_int, c_float, c_float, c_int, c_float, c_float, c_int, c_int, P,
-                               c_uint64, c_int, P, P, P, P, P, P, P]),
+                               c_uint64, P, c_int, P, P, P, P, P, P, P]),
     "ctx_stratified_fwd": (c_int, [P, c_int64, P, c_int64, c_int64, c_int, c_int, c_int, P, c_uint64, P, P]),
     "ctx_ndc_fwd": (c_int, [c_int, c_int, c_float, c_float, P, P, c_int64, P, P, P]),
     "ctx_ndc_bwd": (c_int, [c_int, c_int, c_float, c_float, P, P, P, P, c_int64, P, P, P]),
     "ctx_composite_fwd": (c_int, [P, P, P, P, c_int64, c_int, c_int, P, P, P, P, P, P]),
     "ctx_composite_bwd": (c_int, [P, P, P, P, c_int64, c_int, c_int, P, P, P, P, P, P, P]),
-    "ctx_resample_fwd": (c_int, [P, c_int64, c_int, P, c_int64, P, P, c_int, c_uint64, c_int64, c_int,
+    "ctx_resample_fwd": (c_int, [P, c_int64, c_int, P, c_int64, P, P, c_int, c_uint64, P, c_int64, c_int,
                                  c_int, P, P, P, c_int64, c_int, P, P]),
     "ctx_resample_bwd": (c_int, [P, c_int64, c_int, P, c_int64, P, c_int, c_uint64, c_int64, c_int, c_int,
                                  P, P, P]),
@@ -39,19 +39,24 @@ _SIGNATURES = {
     "ctx_mlp_describe": (c_int, [c_int, ctypes.c_uint32, c_int, c_int, c_int, P]),
     "ctx_mlp_pack": (c_int, [P, P, c_int, P, P, P, P]),
     "ctx_mlp_fwd": (c_int, [P, P, P, c_int, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int64, P, P, P]),
+    "ctx_mlp_fwd_ex": (c_int, [P, P, P, c_int, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int64, P, P, c_int, P]),
     "ctx_mlp_set_prof_buffer": (c_int, [P]),
     "ctx_mlp_set_debug": (c_int, [c_int]),
     "ctx_mlp_set_hang_buffer": (c_int, [P]),
     "ctx_mlp_dgrad": (c_int, [P, P, P, P, P, P, c_int64, P]),
-    "ctx_mlp_wgrad": (c_int, [P, P, P, c_int64, P, c_int, P]),
-    "ctx_mlp_bwd": (c_int, [P, P, P, P, P, P, c_int64, P, c_int, P]),
+    "ctx_mlp_wgrad": (c_int, [P, P, P, c_int64, P, c_int, P, P, P]),
+    "ctx_mlp_bwd": (c_int, [P, P, P, P, P, P, c_int64, P, c_int, P, P, P]),
     "ctx_mlp_dgrad_ex": (c_int, [P, P, P, P, P, P, c_int64, c_int, P]),
-    "ctx_mlp_wgrad_ex": (c_int, [P, P, P, c_int64, P, c_int, c_int, P]),
+    "ctx_mlp_wgrad_ex": (c_int, [P, P, P, c_int64, P, c_int, P, P, c_int, P]),
+    "ctx_mlp_wgrad_scratch_floats": (c_int, []),
+    "ctx_composite_train": (c_int, [P, P, P, P, c_int64, c_int, c_int, P, c_float, P, P, P, P, P]),
     "ctx_texmap_fwd": (c_int, [P, P, P, P, P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, P]),
     "ctx_texmap_bwd": (c_int, [P, P, P, P, c_int64, c_int64, c_int, c_int, c_int, c_int, c_int, P]),
     "ctx_tanh01_fwd": (c_int, [P, P, c_int64, c_int, P]),
     "ctx_tanh01_bwd": (c_int, [P, P, P, P, c_int64, c_int, P]),
     "ctx_adam_step": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_int, c_float, c_float, P]),
+    "ctx_step_tick": (c_int, [P, P, P]),
+    "ctx_adam_step_dev": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, P, c_float, c_float, P]),
     "ctx_mse_fwd_bwd": (c_int, [P, P, P, c_int64, c_float, P, P, P, P]),
     "ctx_tcgen05_selftest": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     "ctx_tcgen05_mma_rate": (c_int, [c_int, c_int, c_int, c_int, P, c_int, P, P]),
@@ -93,7 +98,7 @@ def check(code: int, what: str) -> None:
 
 
 # kernels launched per ABI call (bench.py reports the total as gpu_launches)
-KERNELS_PER_CALL = {"ctx_mlp_bwd": 2}
+KERNELS_PER_CALL = {"ctx_mlp_bwd": 2}     # (the view-direction wgrad also runs a small post kernel: +1, counted by the callers that know the net)
 launch_count = 0
 
 

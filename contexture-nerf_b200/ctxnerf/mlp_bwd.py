@@ -36,15 +36,24 @@ def mlp_dgrad(module, packed, acts, P, g_out, max_sms=0):
     return dacts
 
 
-def mlp_wgrad(module, acts, dacts, P, sinks=None, max_sms=0):
+def wgrad_scratch(dev):
+    """fp32 scratch of the view-direction head's G job (ctx_mlp_wgrad_scratch_floats floats; zeroed by the launcher)."""
+    from . import _lib
+    return torch.empty(_lib.lib().ctx_mlp_wgrad_scratch_floats(), device=dev, dtype=torch.float32)
+
+
+def mlp_wgrad(module, acts, dacts, P, sinks=None, max_sms=0, scratch=None):
     """Parameter gradients from the activation and dZ records (ctx_mlp_wgrad_ex); accumulates into ``sinks`` when
     given (returns None), else returns fresh tensors."""
     dev = acts.device
     grads, params = _grad_targets(module, sinks, dev)
     arr = (ctypes.c_void_p * len(grads))(*[t.data_ptr() for t in grads])
+    parr = (ctypes.c_void_p * len(params))(*[t.data_ptr() for t in params])
+    if scratch is None and module._desc.in_views > 0:
+        scratch = wgrad_scratch(dev)
     with torch.cuda.device(dev):
         call("ctx_mlp_wgrad_ex", module._desc.p, ptr(acts), ptr(dacts), P, ctypes.cast(arr, ctypes.c_void_p),
-             len(grads), int(max_sms), stream_ptr(dev))
+             len(grads), ctypes.cast(parr, ctypes.c_void_p), ptr(scratch), int(max_sms), stream_ptr(dev))
     if sinks is not None:
         return None
     return [gr if p.requires_grad else None for gr, p in zip(grads, params)]

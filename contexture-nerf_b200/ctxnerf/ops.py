@@ -141,7 +141,7 @@ class _Resample(torch.autograd.Function):
         out = torch.empty(R, n_samples, device=dev, dtype=torch.float32)
         with torch.cuda.device(dev):
             call("ctx_resample_fwd", ptr(b2), b2.stride(0) if R > 1 else b2.shape[-1], int(mid_bins), ptr(w2),
-                 w2.stride(0) if R > 1 else nw, None, ptr(u2), int(det), seed, R, B, n_samples, ptr(out),
+                 w2.stride(0) if R > 1 else nw, None, ptr(u2), int(det), seed, None, R, B, n_samples, ptr(out),
                  None, None, 0, 0, None, stream_ptr(dev))
         ctx.save_for_backward(b2, w2, u2 if u2 is not None else torch.empty(0, device=dev))
         ctx.meta = (R, B, n_samples, det, seed, mid_bins, u2 is not None, weights.shape)
@@ -168,7 +168,7 @@ def resample(bins, weights, n_samples, det=False, u=None, seed=None, mid_bins=Fa
 
 
 def resample_merge(z_vals, weights, n_importance, det=False, u=None, seed=None, cdf=None,
-                   return_inds=False):
+                   return_inds=False, seed_dev=None, out=None):
     """Fused hierarchical step of upstream render_rays (no grad, as upstream
     detaches): bins = mid-points of z_vals, pdf = weights[...,1:-1];
     returns (z_samples [R,Ni], z_all [R,S+Ni] sorted[, inds])."""
@@ -179,16 +179,19 @@ def resample_merge(z_vals, weights, n_importance, det=False, u=None, seed=None, 
     R, S = z2.shape
     B = S - 1
     if seed is None:
-        seed = 0 if (det or u is not None) else new_seed()
+        seed = 0 if (det or u is not None or seed_dev is not None) else new_seed()
     u2 = _f32c(u.reshape(R, n_importance)) if u is not None else None
     c2 = _f32c(cdf.reshape(R, B)) if cdf is not None else None
-    zs = torch.empty(R, n_importance, device=dev, dtype=torch.float32)
-    z_all = torch.empty(R, S + n_importance, device=dev, dtype=torch.float32)
+    if out is not None:          # caller-owned (static) outputs: the captured training step
+        zs, z_all = out
+    else:
+        zs = torch.empty(R, n_importance, device=dev, dtype=torch.float32)
+        z_all = torch.empty(R, S + n_importance, device=dev, dtype=torch.float32)
     inds = torch.empty(R, n_importance, device=dev, dtype=torch.int64) if return_inds else None
     w_view = w2[:, 1:-1]  # stride S, offset 1: no copy
     with torch.cuda.device(dev):
-        call("ctx_resample_fwd", ptr(z2), S, 1, ptr(w_view), S, ptr(c2), ptr(u2), int(det), int(seed), R, B,
-             n_importance, ptr(zs), ptr(inds), ptr(z2), S, S, ptr(z_all), stream_ptr(dev))
+        call("ctx_resample_fwd", ptr(z2), S, 1, ptr(w_view), S, ptr(c2), ptr(u2), int(det), int(seed), ptr(seed_dev),
+             R, B, n_importance, ptr(zs), ptr(inds), ptr(z2), S, S, ptr(z_all), stream_ptr(dev))
     if return_inds:
         return zs, z_all, inds
     return zs, z_all
@@ -206,7 +209,7 @@ def resample_raw(bins, weights, n_samples, det=True, u=None, cdf=None, seed=0):
     out = torch.empty(R, n_samples, device=dev, dtype=torch.float32)
     inds = torch.empty(R, n_samples, device=dev, dtype=torch.int64)
     with torch.cuda.device(dev):
-        call("ctx_resample_fwd", ptr(b2), B, 0, ptr(w2), B - 1, ptr(c2), ptr(u2), int(det), int(seed), R, B,
+        call("ctx_resample_fwd", ptr(b2), B, 0, ptr(w2), B - 1, ptr(c2), ptr(u2), int(det), int(seed), None, R, B,
              n_samples, ptr(out), ptr(inds), None, 0, 0, None, stream_ptr(dev))
     return out, inds
 
@@ -214,7 +217,7 @@ def resample_raw(bins, weights, n_samples, det=True, u=None, cdf=None, seed=0):
 # ------------------------------------------------------------------ raygen ---
 def raygen(H, W, K, c2w, *, device=None, ray_idx=None, ndc=None, n_samples=0, near=0.0, far=1.0,
            lindisp=False, perturb=False, jitter=None, seed=None, sphere=None, want_viewdirs=False,
-           want_near_far=False):
+           want_near_far=False, seed_dev=None, out=None):
     """Fused get_rays (+ndc) (+viewdirs) (+stratified z_vals).  Returns a dict."""
     if torch.is_tensor(c2w):
         dev = c2w.device if c2w.is_cuda else torch.device(device or "cuda")
@@ -233,12 +236,15 @@ def raygen(H, W, K, c2w, *, device=None, ray_idx=None, ndc=None, n_samples=0, ne
         n = ray_idx.numel()
     else:
         n = H * W
-    o = torch.empty(n, 3, device=dev, dtype=torch.float32)
-    d = torch.empty(n, 3, device=dev, dtype=torch.float32)
-    v = torch.empty(n, 3, device=dev, dtype=torch.float32) if want_viewdirs else None
-    z = torch.empty(n, n_samples, device=dev, dtype=torch.float32) if n_samples > 0 else None
+    if out is not None:          # caller-owned (static) outputs: (rays_o, rays_d, viewdirs, z_vals)
+        o, d, v, z = out
+    else:
+        o = torch.empty(n, 3, device=dev, dtype=torch.float32)
+        d = torch.empty(n, 3, device=dev, dtype=torch.float32)
+        v = torch.empty(n, 3, device=dev, dtype=torch.float32) if want_viewdirs else None
+        z = torch.empty(n, n_samples, device=dev, dtype=torch.float32) if n_samples > 0 else None
     nf = torch.empty(n, 2, device=dev, dtype=torch.float32) if want_near_far else None
-    if perturb and jitter is None and seed is None:
+    if perturb and jitter is None and seed is None and seed_dev is None:
         seed = new_seed()
     import ctypes
     sph = (ctypes.c_float * 4)(*[float(s) for s in sphere]) if sphere is not None else None
@@ -247,7 +253,7 @@ def raygen(H, W, K, c2w, *, device=None, ray_idx=None, ndc=None, n_samples=0, ne
     with torch.cuda.device(dev):
         call("ctx_raygen_fwd", int(H), int(W), fx, fy, cx, cy, ptr(c2w_d), int(ld), ptr(ray_idx), n, use_ndc,
              nfoc, nnear, int(n_samples), float(near), float(far), int(lindisp), int(bool(perturb)),
-             ptr(jitter), int(seed or 0), int(sphere is not None),
+             ptr(jitter), int(seed or 0), ptr(seed_dev), int(sphere is not None),
              ctypes.cast(sph, ctypes.c_void_p) if sph is not None else None,
              ptr(o), ptr(d), ptr(v), ptr(z), ptr(nf), stream_ptr(dev))
     return {"rays_o": o, "rays_d": d, "viewdirs": v, "z_vals": z, "near_far": nf}

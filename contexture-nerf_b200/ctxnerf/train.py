@@ -2,27 +2,69 @@
 kernels -- the hot path BASELINE.json measures.
 
 One step = ray generation fused with stratified sampling -> coarse MLP (points
-encoded in shared memory) -> raw2outputs -> sample_pdf + merge -> fine MLP ->
-raw2outputs -> img2mse(rgb)+img2mse(rgb0) -> hand-written backward of every
-stage -> one gradient all-reduce -> Adam.  It is upstream's render()+train
-iteration with the same hyper-parameter names; every numeric
-stage is a libctxnerf.so kernel, orchestrated here without autograd.
+encoded in shared memory) -> raw2outputs fused with the loss and its own
+backward -> sample_pdf + merge -> fine MLP -> fused raw2outputs/loss/backward ->
+hand-written MLP backward (dgrad, wgrad) of both networks -> one gradient
+all-reduce -> Adam -> re-pack of the bf16 weight streams.  It is upstream's
+render()+train iteration (SURVEY.md 3.2) with the same hyper-parameter names;
+every numeric stage is a libctxnerf.so kernel, orchestrated here without
+autograd.
+
+The step works on STATIC buffers (allocated once per batch size) and keeps its
+per-step state -- Philox seed offset, Adam step count, loss -- on the device, so
+the whole launch sequence is captured once into a CUDA graph and replayed
+(SURVEY.md 8f row 3): no host-side argument changes between steps.
 """
 from __future__ import annotations
 
 import ctypes
-from typing import Optional
-
 import os
+from typing import Optional
 
 import torch
 
-from . import ops
+from . import _lib, ops
 from ._lib import CtxNerfError, call, ptr, stream_ptr
 from .dist import FlatBucket, world
-from .mlp import forward_raw
-from .mlp_bwd import mlp_backward, mlp_dgrad, mlp_wgrad
+from .mlp import TILE, forward_raw, pack_into
+from .mlp_bwd import wgrad_scratch
 from .run_nerf_helpers import NeRF
+
+
+def _env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return int(default)
+
+
+class _Plan:
+    """Static device buffers of the training step for one batch size R."""
+
+    def __init__(self, tr: "NerfTrainer", R: int):
+        dev, S, Sf = tr.device, tr.N_samples, tr.N_samples + tr.N_importance
+        f32 = dict(device=dev, dtype=torch.float32)
+        self.R = R
+        self.idx = torch.zeros(R, device=dev, dtype=torch.int64)
+        self.target = torch.zeros(R, 3, **f32)
+        self.o, self.d, self.v = (torch.empty(R, 3, **f32) for _ in range(3))
+        self.z_c, self.w_c = torch.empty(R, S, **f32), torch.empty(R, S, **f32)
+        self.raw_c, self.g_raw_c = torch.empty(R * S, 4, **f32), torch.empty(R * S, 4, **f32)
+        self.zs, self.z_f = torch.empty(R, tr.N_importance, **f32), torch.empty(R, Sf, **f32)
+        self.raw_f, self.g_raw_f = torch.empty(R * Sf, 4, **f32), torch.empty(R * Sf, 4, **f32)
+        self.rgb0, self.rgb = torch.empty(R, 3, **f32), torch.empty(R, 3, **f32)
+
+        def records(P, net):
+            ntiles = 4 * ((P + 4 * TILE - 1) // (4 * TILE))     # the 2-CTA kernels work on 4 tiles at a time
+            n = ntiles * net._desc.act_tile_bytes
+            return (torch.empty(n, dtype=torch.uint8, device=dev), torch.empty(n, dtype=torch.uint8, device=dev))
+
+        self.acts_c, self.dacts_c = records(R * S, tr.coarse)
+        self.acts_f, self.dacts_f = records(R * Sf, tr.fine)
+        self.graph = None          # torch.cuda.CUDAGraph of the step (None: not captured yet)
+        self.graph_tail = None     # second graph (Adam + re-pack) when the all-reduce runs between the two
+        self.eager_steps = 0
+        self.kernels_per_step = 0
 
 
 class NerfTrainer:
@@ -30,8 +72,9 @@ class NerfTrainer:
                  white_bkgd=True, lindisp=False, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, device=None, seed=0,
                  multires=10, multires_views=4):
         self.device = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        dev = self.device
         self.H, self.W, self.K = H, W, K
-        self.c2w = torch.as_tensor(c2w, dtype=torch.float32).to(self.device).contiguous()
+        self.c2w = torch.as_tensor(c2w, dtype=torch.float32).to(dev).contiguous()
         self.near, self.far = float(near), float(far)
         self.N_samples, self.N_importance = int(N_samples), int(N_importance)
         self.perturb, self.white_bkgd, self.lindisp = float(perturb), bool(white_bkgd), bool(lindisp)
@@ -40,8 +83,8 @@ class NerfTrainer:
         st = torch.random.get_rng_state()
         torch.manual_seed(seed)
         in_pts, in_views = 3 * (1 + 2 * multires), 3 * (1 + 2 * multires_views)
-        self.coarse = NeRF(input_ch=in_pts, input_ch_views=in_views).to(self.device)
-        self.fine = NeRF(input_ch=in_pts, input_ch_views=in_views).to(self.device)
+        self.coarse = NeRF(input_ch=in_pts, input_ch_views=in_views).to(dev)
+        self.fine = NeRF(input_ch=in_pts, input_ch_views=in_views).to(dev)
         torch.random.set_rng_state(st)
         for net in (self.coarse, self.fine):
             net.L_pts, net.L_dirs = multires, multires_views
@@ -49,15 +92,44 @@ class NerfTrainer:
         self.bucket = FlatBucket([self.coarse, self.fine])
         self.exp_avg = torch.zeros_like(self.bucket.flat)
         self.exp_avg_sq = torch.zeros_like(self.bucket.flat)
-        self.step_count = 0
         self.rank, self.world_size = world()
-        self._loss = torch.zeros(1, device=self.device)
-        self.timers = None      # optional dict name -> list[(start_event, end_event)]
-        # backward overlap (see step): side stream + SM budget of the coarse chain
+        self._loss = torch.zeros(1, device=dev)
+        # device-side step state: [0] Philox seed offset, [1] Adam step count (ctx_step_tick advances both)
+        self._ctr = torch.zeros(2, device=dev, dtype=torch.int64)
+        # the Philox base seed comes from torch's generator: torch.manual_seed makes a training run reproducible
+        self._seed0 = ops.new_seed() if self.perturb > 0.0 else 0
+        # bf16 weight streams of both networks: trainer-owned static buffers, re-packed after every Adam update
+        self._pk = {}
+        for net in (self.coarse, self.fine):
+            d = net._desc
+            self._pk[net] = (torch.empty(d.w_bytes, dtype=torch.uint8, device=dev),
+                             torch.empty(max(d.wt_bytes, 16), dtype=torch.uint8, device=dev),
+                             torch.empty(d.n_fparams, dtype=torch.float32, device=dev))
+        self._scratch = {net: wgrad_scratch(dev) for net in (self.coarse, self.fine)}
+        self._packed_version = -1
+        self._plans = {}
+        self.timers = None      # optional dict name -> list[(start_event, end_event)]; forces the eager path
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        self.n_sms = n_sm
+        # Backward schedule: the two networks' chains are independent and their kernels bind on different resources
+        # (dgrad: tensor pipe / epilogue; wgrad: HBM reads).  The coarse chain runs on a side stream inside an SM
+        # budget while wgrad of the fine network streams its records through the other SMs.
         self.overlap_backward = os.environ.get("CTXNERF_OVERLAP", "1") != "0"
-        self.side_sms = int(os.environ.get("CTXNERF_SIDE_SMS", "44"))
-        self._side = torch.cuda.Stream(device=self.device)
-        self._ev0, self._ev1 = torch.cuda.Event(), torch.cuda.Event()
+        self.side_sms = _env_int("CTXNERF_SIDE_SMS", 44)
+        # CTXNERF_EARLY_COARSE=1: start the coarse backward chain right after the coarse compositing (its loss term
+        # does not depend on the fine pass), beside resample + fwd_fine + dgrad_fine, which then take main_sms SMs
+        self.early_coarse = os.environ.get("CTXNERF_EARLY_COARSE", "0") == "1"
+        self.main_sms = _env_int("CTXNERF_MAIN_SMS", n_sm - self.side_sms)
+        self.use_graph = os.environ.get("CTXNERF_GRAPH", "1") != "0"
+        self._side = torch.cuda.Stream(device=dev)
+        self._pack_stream = torch.cuda.Stream(device=dev)
+        self._ev0, self._ev1, self._ev2, self._ev3 = (torch.cuda.Event() for _ in range(4))
+        with torch.cuda.device(dev):
+            self._repack()
+
+    @property
+    def step_count(self) -> int:
+        return int(self._ctr[1].item())
 
     # ------------------------------------------------------------------ utils
     def _timed(self, name, fn):
@@ -70,22 +142,223 @@ class NerfTrainer:
         self.timers.setdefault(name, []).append((a, b))
         return r
 
-    def _render(self, ray_idx, save_acts, seed, perturb):
-        S, Ni = self.N_samples, self.N_importance
+    def _repack(self):
+        """bf16 operand images of both networks from the fp32 bucket (two independent launches: the fine network's
+        on a side stream)."""
+        dev = self.device
+        main = torch.cuda.current_stream(dev)
+        self._ev2.record(main)
+        self._pack_stream.wait_event(self._ev2)
+        with torch.cuda.stream(self._pack_stream):
+            pack_into(self.fine._desc, self.fine._param_list(), self._pk[self.fine])
+            self._ev3.record(self._pack_stream)
+        pack_into(self.coarse._desc, self.coarse._param_list(), self._pk[self.coarse])
+        main.wait_event(self._ev3)
+
+    def _fwd(self, net, rays, P, out, acts, max_sms=0):
+        o, d, v, z = rays
+        w, _, f = self._pk[net]
+        call("ctx_mlp_fwd_ex", net._desc.p, ptr(w), ptr(f), 1, None, 0, ptr(o), ptr(d), ptr(v), ptr(z), z.shape[-1],
+             net.L_pts, net.L_dirs, P, ptr(out), ptr(acts), int(max_sms), stream_ptr(self.device))
+
+    def _dgrad(self, net, g_raw, acts, dacts, P, max_sms=0):
+        _, wt, f = self._pk[net]
+        call("ctx_mlp_dgrad_ex", net._desc.p, ptr(wt), ptr(f), ptr(g_raw), ptr(acts), ptr(dacts), P, int(max_sms),
+             stream_ptr(self.device))
+
+    def _wgrad(self, net, acts, dacts, P, max_sms=0):
+        sinks, params = self.bucket.sinks_for(net), net._param_list()
+        garr = (ctypes.c_void_p * len(sinks))(*[t.data_ptr() for t in sinks])
+        parr = (ctypes.c_void_p * len(params))(*[t.data_ptr() for t in params])
+        _lib.launch_count += 1     # the view-direction head's post kernel
+        call("ctx_mlp_wgrad_ex", net._desc.p, ptr(acts), ptr(dacts), P, ctypes.cast(garr, ctypes.c_void_p), len(sinks),
+             ctypes.cast(parr, ctypes.c_void_p), ptr(self._scratch[net]), int(max_sms), stream_ptr(self.device))
+
+    def _comp_train(self, raw, z, d, R, S, target, g_raw, weights, rgb):
+        call("ctx_composite_train", ptr(raw), ptr(z), ptr(d), None, R, S, int(self.white_bkgd), ptr(target),
+             1.0 / (3.0 * R), ptr(self._loss), ptr(g_raw), ptr(weights), ptr(rgb), stream_ptr(self.device))
+
+    # --------------------------------------------------------- the step body
+    def _enqueue_head(self, pl: _Plan):
+        """Everything up to (and including) the weight gradients, on the current stream (+ the side stream)."""
+        dev, R, S, Ni = self.device, pl.R, self.N_samples, self.N_importance
+        Sf, Pc, Pf = S + Ni, pl.R * S, pl.R * (S + Ni)
+        jit = self.perturb > 0.0
+        main = torch.cuda.current_stream(dev)
+        early = self.overlap_backward and self.early_coarse
+        call("ctx_step_tick", ptr(self._ctr), ptr(self._loss), stream_ptr(dev))
+        self.bucket.zero_grad()
+        ops.raygen(self.H, self.W, self.K, self.c2w, ray_idx=pl.idx, n_samples=S, near=self.near, far=self.far,
+                   lindisp=self.lindisp, perturb=jit, seed=self._seed0, seed_dev=self._ctr if jit else None,
+                   want_viewdirs=True, out=(pl.o, pl.d, pl.v, pl.z_c))
+        rays_c, rays_f = (pl.o, pl.d, pl.v, pl.z_c), (pl.o, pl.d, pl.v, pl.z_f)
+        self._timed("mlp_fwd_coarse", lambda: self._fwd(self.coarse, rays_c, Pc, pl.raw_c, pl.acts_c))
+        # raw2outputs + img2mse(rgb0, target) + their backward in one pass; the weights feed sample_pdf
+        self._comp_train(pl.raw_c, pl.z_c, pl.d, R, S, pl.target, pl.g_raw_c, pl.w_c, pl.rgb0)
+
+        def coarse_chain(dgrad_sms, wgrad_sms=0):
+            self._timed("mlp_dgrad_coarse",
+                        lambda: self._dgrad(self.coarse, pl.g_raw_c, pl.acts_c, pl.dacts_c, Pc, max_sms=dgrad_sms))
+            self._timed("mlp_wgrad_coarse",
+                        lambda: self._wgrad(self.coarse, pl.acts_c, pl.dacts_c, Pc, max_sms=wgrad_sms))
+
+        if early:
+            self._ev0.record(main)
+            self._side.wait_event(self._ev0)
+            with torch.cuda.stream(self._side):
+                coarse_chain(self.side_sms, self.side_sms)
+                self._ev1.record(self._side)
+        ops.resample_merge(pl.z_c, pl.w_c, Ni, det=not jit, seed=self._seed0 + 1, seed_dev=self._ctr if jit else None,
+                           out=(pl.zs, pl.z_f))
+        msm = self.main_sms if early else 0
+        self._timed("mlp_fwd_fine", lambda: self._fwd(self.fine, rays_f, Pf, pl.raw_f, pl.acts_f, max_sms=msm))
+        self._comp_train(pl.raw_f, pl.z_f, pl.d, R, Sf, pl.target, pl.g_raw_f, None, pl.rgb)
+        self._timed("mlp_dgrad_fine",
+                    lambda: self._dgrad(self.fine, pl.g_raw_f, pl.acts_f, pl.dacts_f, Pf, max_sms=msm))
+        if early:
+            self._timed("mlp_wgrad_fine", lambda: self._wgrad(self.fine, pl.acts_f, pl.dacts_f, Pf))
+            main.wait_event(self._ev1)
+        elif self.overlap_backward:
+            self._ev0.record(main)
+            self._side.wait_event(self._ev0)
+            if self.timers is not None:
+                g0 = torch.cuda.Event(enable_timing=True)
+                g0.record(main)
+            with torch.cuda.stream(self._side):
+                coarse_chain(self.side_sms)
+                self._ev1.record(self._side)
+            self._timed("mlp_wgrad_fine", lambda: self._wgrad(self.fine, pl.acts_f, pl.dacts_f, Pf,
+                                                              max_sms=self.n_sms - self.side_sms))
+            main.wait_event(self._ev1)
+            if self.timers is not None:   # span of the concurrent group on the main stream
+                g1 = torch.cuda.Event(enable_timing=True)
+                g1.record(main)
+                self.timers.setdefault("bwd_overlap_group", []).append((g0, g1))
+        else:
+            self._timed("mlp_wgrad_fine", lambda: self._wgrad(self.fine, pl.acts_f, pl.dacts_f, Pf))
+            coarse_chain(0)
+
+    def _enqueue_tail(self):
+        dev = self.device
+        call("ctx_adam_step_dev", ptr(self.bucket.flat), ptr(self.bucket.grad), ptr(self.exp_avg),
+             ptr(self.exp_avg_sq), self.bucket.numel, self.lr, self.betas[0], self.betas[1], self.eps, ptr(self._ctr),
+             0.0, 1.0 / self.world_size, stream_ptr(dev))
+        self._repack()
+
+    def _plan(self, R: int) -> _Plan:
+        pl = self._plans.get(R)
+        if pl is None:
+            pl = self._plans[R] = _Plan(self, R)
+        return pl
+
+    # ------------------------------------------------------------------- API
+    @torch.no_grad()
+    def step(self, ray_idx: torch.Tensor, target: torch.Tensor, optimizer_step: bool = True) -> torch.Tensor:
+        """One training step on this rank's ray batch; returns the loss (device scalar, valid once the stream has
+        reached the end of the step)."""
+        dev = self.device
+        if not (torch.is_tensor(target) and target.is_cuda and target.device == dev):
+            raise CtxNerfError("NerfTrainer.step: target must be a CUDA tensor on the trainer's device "
+                               "(use step_from_host for host buffers)")
+        if not (torch.is_tensor(ray_idx) and ray_idx.is_cuda and ray_idx.device == dev):
+            raise CtxNerfError("NerfTrainer.step: ray_idx must be a CUDA tensor on the trainer's device")
+        R = ray_idx.numel()
+        if target.numel() != 3 * R:
+            raise CtxNerfError("NerfTrainer.step: target must hold one rgb triple per ray")
+        if R == 0:
+            return self._loss.zero_()
+        with torch.cuda.device(dev):
+            pl = self._plan(R)
+            pl.idx.copy_(ray_idx.reshape(-1), non_blocking=True)
+            pl.target.copy_(target.reshape(R, 3), non_blocking=True)     # (casts a non-fp32 target)
+            self._run(pl, optimizer_step)
+        return self._loss
+
+    def _run(self, pl: _Plan, optimizer_step: bool):
+        multi = self.world_size > 1
+        if optimizer_step:     # the modules' own pack caches (direct net(x) calls) do not see the in-place Adam update
+            self.coarse._packed.invalidate()
+            self.fine._packed.invalidate()
+        graphable = self.use_graph and self.timers is None and optimizer_step
+        if not graphable or pl.eager_steps < 1:
+            # eager launch sequence (first step of a batch size: sets the kernels' attributes; timed passes)
+            l0 = _lib.launch_count
+            self._enqueue_head(pl)
+            self.bucket.all_reduce()
+            if optimizer_step:
+                self._enqueue_tail()
+            if graphable:
+                pl.eager_steps += 1
+                pl.kernels_per_step = _lib.launch_count - l0
+            return
+        if pl.graph is None:
+            self._capture(pl, multi)
+        _lib.launch_count += pl.kernels_per_step
+        pl.graph.replay()
+        if multi:
+            self.bucket.all_reduce()
+            pl.graph_tail.replay()
+
+    def _capture(self, pl: _Plan, multi: bool):
+        """Capture the step into one CUDA graph (single process) or two with the all-reduce between them."""
+        dev = self.device
+        torch.cuda.synchronize(dev)
+        saved = _lib.launch_count
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._enqueue_head(pl)
+                if not multi:
+                    self._enqueue_tail()
+            tail = None
+            if multi:
+                tail = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(tail, capture_error_mode="thread_local"):
+                    self._enqueue_tail()
+        except Exception as e:                      # pragma: no cover - depends on driver / NCCL state
+            raise CtxNerfError(f"CUDA-graph capture of the training step failed ({e}); set CTXNERF_GRAPH=0 to run the "
+                               "eager launch sequence") from e
+        finally:
+            _lib.launch_count = saved
+        pl.graph, pl.graph_tail = g, tail
+
+    def step_from_host(self, ray_idx_pinned: torch.Tensor, target_pinned: torch.Tensor,
+                       loss_pinned: torch.Tensor) -> "torch.cuda.Event":
+        """End-to-end entry: host (pinned) inputs in, loss back to the host.  Asynchronous: the returned event marks
+        the arrival of the loss in ``loss_pinned``, so a training loop can submit step i+1 before it reads the loss
+        of step i (the launches of the next step then hide behind the GPU work of this one)."""
+        dev = self.device
+        R = ray_idx_pinned.numel()
+        if target_pinned.numel() != 3 * R:
+            raise CtxNerfError("NerfTrainer.step_from_host: target must hold one rgb triple per ray")
+        with torch.cuda.device(dev):
+            pl = self._plan(R)
+            pl.idx.copy_(ray_idx_pinned.reshape(-1), non_blocking=True)              # host -> device, inside the step
+            pl.target.copy_(target_pinned.reshape(R, 3), non_blocking=True)
+            self._run(pl, True)
+            loss_pinned.copy_(self._loss, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(dev))
+        return done     # loss_pinned is valid once this event has completed
+
+    # ------------------------------------------------------------ inference
+    def _render(self, ray_idx, perturb, seed=0, max_sms=0):
+        """Forward-only coarse+fine render of the given pixels (None = the whole image): dynamic shapes, fresh
+        outputs; shares the trainer's packed weights."""
+        dev, S, Ni = self.device, self.N_samples, self.N_importance
         jit = bool(perturb)
         r = ops.raygen(self.H, self.W, self.K, self.c2w, ray_idx=ray_idx, n_samples=S, near=self.near, far=self.far,
                        lindisp=self.lindisp, perturb=jit, seed=seed, want_viewdirs=True)
         o, d, v, z_c = r["rays_o"], r["rays_d"], r["viewdirs"], r["z_vals"]
         R = o.shape[0]
-        raw_c, acts_c, Pc, pk_c = self._timed("mlp_fwd_coarse",
-                                              lambda: forward_raw(self.coarse, rays=(o, d, v, z_c), save_acts=save_acts))
+        raw_c = torch.empty(R * S, 4, device=dev)
+        self._fwd(self.coarse, (o, d, v, z_c), R * S, raw_c, None, max_sms)
         comp_c = self._composite(raw_c, z_c, d, R, S)
         zs, z_f = ops.resample_merge(z_c, comp_c[3], Ni, det=not jit, seed=seed + 1)
-        raw_f, acts_f, Pf, pk_f = self._timed("mlp_fwd_fine",
-                                              lambda: forward_raw(self.fine, rays=(o, d, v, z_f), save_acts=save_acts))
+        raw_f = torch.empty(R * (S + Ni), 4, device=dev)
+        self._fwd(self.fine, (o, d, v, z_f), R * (S + Ni), raw_f, None, max_sms)
         comp_f = self._composite(raw_f, z_f, d, R, S + Ni)
-        return dict(d=d, z_c=z_c, z_f=z_f, raw_c=raw_c, raw_f=raw_f, acts_c=acts_c, acts_f=acts_f, Pc=Pc, Pf=Pf,
-                    pk_c=pk_c, pk_f=pk_f, comp_c=comp_c, comp_f=comp_f, R=R)
+        return dict(comp_c=comp_c, comp_f=comp_f, z_f=z_f, raw_f=raw_f, R=R)
 
     def _composite(self, raw, z, d, R, S):
         dev = self.device
@@ -98,111 +371,30 @@ class NerfTrainer:
              ptr(acc), ptr(w), ptr(depth), stream_ptr(dev))
         return rgb, disp, acc, w, depth
 
-    def _composite_bwd(self, raw, z, d, R, S, g_rgb):
-        g_raw = torch.empty_like(raw)
-        call("ctx_composite_bwd", ptr(raw), ptr(z), ptr(d), None, R, S, int(self.white_bkgd), ptr(g_rgb), None,
-             None, None, None, ptr(g_raw), stream_ptr(self.device))
-        return g_raw
-
-    # ------------------------------------------------------------------- API
     @torch.no_grad()
     def render(self, ray_idx: Optional[torch.Tensor] = None):
-        """Inference render of the given pixels (None = the whole H x W image)."""
+        """Inference render of the given pixels (None = the whole H x W image).  Deterministic, as upstream's
+        render_kwargs_test (perturb=False, raw_noise_std=0): linspace depths and det=True importance sampling."""
         with torch.cuda.device(self.device):
-            # evaluation is deterministic, as upstream's render_kwargs_test (perturb=False, raw_noise_std=0):
-            # linspace depths and det=True importance sampling; the jitter belongs to step() only
-            fwd = self._render(ray_idx, save_acts=False, seed=0, perturb=False)
+            fwd = self._render(ray_idx, perturb=False)
         rgb, disp, acc, _, depth = fwd["comp_f"]
         return dict(rgb_map=rgb, disp_map=disp, acc_map=acc, depth_map=depth, rgb0=fwd["comp_c"][0])
 
     @torch.no_grad()
-    def render_view(self, H, W, K, c2w, n_samples=192, sphere=None, near=None, far=None):
-        """Single-pass render of a whole view with the fine network (BASELINE config 4: per-ray near/far from
-        the bounding sphere of the normalised mesh, `n_samples` depths per ray, no hierarchical pass)."""
+    def render_view(self, H, W, K, c2w, n_samples=192, sphere=None, near=None, far=None, ray_idx=None):
+        """Single-pass render of a view (or of the pixels ``ray_idx`` of it) with the fine network (BASELINE config 4:
+        per-ray near/far from the bounding sphere of the normalised mesh, `n_samples` depths per ray, no hierarchical
+        pass).  Maps are [H,W,...] for a whole view, [n,...] for a pixel list."""
         dev = self.device
         with torch.cuda.device(dev):
             r = ops.raygen(H, W, K, torch.as_tensor(c2w, dtype=torch.float32).to(dev), n_samples=n_samples,
                            near=self.near if near is None else near, far=self.far if far is None else far,
-                           sphere=sphere, want_viewdirs=True)
-            raw, _, _, _ = forward_raw(self.fine, rays=(r["rays_o"], r["rays_d"], r["viewdirs"], r["z_vals"]))
-            rgb, disp, acc, _, depth = self._composite(raw, r["z_vals"], r["rays_d"], H * W, n_samples)
-        return dict(rgb_map=rgb.reshape(H, W, 3), disp_map=disp.reshape(H, W), acc_map=acc.reshape(H, W),
-                    depth_map=depth.reshape(H, W))
-
-    @torch.no_grad()
-    def step(self, ray_idx: torch.Tensor, target: torch.Tensor, optimizer_step: bool = True) -> torch.Tensor:
-        """One training step on this rank's ray batch; returns the loss (device scalar)."""
-        dev = self.device
-        if not (torch.is_tensor(target) and target.is_cuda and target.device == dev):
-            raise CtxNerfError("NerfTrainer.step: target must be a CUDA tensor on the trainer's device "
-                               "(use step_from_host for host buffers)")
-        target = ops._f32c(target)
-        if target.numel() != 3 * ray_idx.numel():
-            raise CtxNerfError("NerfTrainer.step: target must hold one rgb triple per ray")
-        with torch.cuda.device(dev):
-            seed = ops.new_seed() if self.perturb > 0.0 else 0
-            self.bucket.zero_grad()
-            f = self._render(ray_idx, save_acts=True, seed=seed, perturb=self.perturb > 0.0)
-            R, S, Sf = f["R"], self.N_samples, self.N_samples + self.N_importance
-            g_rgb = torch.empty(R, 3, device=dev)
-            g_rgb0 = torch.empty(R, 3, device=dev)
-            call("ctx_mse_fwd_bwd", ptr(f["comp_f"][0]), ptr(f["comp_c"][0]), ptr(target), R * 3, 1.0,
-                 ptr(self._loss), ptr(g_rgb), ptr(g_rgb0), stream_ptr(dev))
-            g_raw_f = self._composite_bwd(f["raw_f"], f["z_f"], f["d"], R, Sf, g_rgb)
-            g_raw_c = self._composite_bwd(f["raw_c"], f["z_c"], f["d"], R, S, g_rgb0)
-            sinks_f, sinks_c = self.bucket.sinks_for(self.fine), self.bucket.sinks_for(self.coarse)
-            dacts_f = self._timed("mlp_dgrad_fine",
-                                  lambda: mlp_dgrad(self.fine, f["pk_f"], f["acts_f"], f["Pf"], g_raw_f))
-            if self.overlap_backward:
-                # The two networks' backward chains are independent, and their kernels bind on different
-                # resources: dgrad on the tensor pipe / epilogue, wgrad on HBM reads.  The coarse chain runs on a
-                # side stream inside a 36-SM budget while wgrad of the fine network streams its records through
-                # the other 112 SMs; wgrad of the coarse network follows on whatever SMs come free.
-                main = torch.cuda.current_stream(dev)
-                self._ev0.record(main)
-                self._side.wait_event(self._ev0)
-                if self.timers is not None:
-                    g0 = torch.cuda.Event(enable_timing=True)
-                    g0.record(main)
-                with torch.cuda.stream(self._side):
-                    dacts_c = self._timed("mlp_dgrad_coarse",
-                                          lambda: mlp_dgrad(self.coarse, f["pk_c"], f["acts_c"], f["Pc"], g_raw_c,
-                                                            max_sms=self.side_sms))
-                    self._timed("mlp_wgrad_coarse",
-                                lambda: mlp_wgrad(self.coarse, f["acts_c"], dacts_c, f["Pc"], sinks_c))
-                    self._ev1.record(self._side)
-                self._timed("mlp_wgrad_fine",
-                            lambda: mlp_wgrad(self.fine, f["acts_f"], dacts_f, f["Pf"], sinks_f,
-                                              max_sms=148 - self.side_sms))
-                main.wait_event(self._ev1)
-                if self.timers is not None:   # span of the concurrent group on the main stream
-                    g1 = torch.cuda.Event(enable_timing=True)
-                    g1.record(main)
-                    self.timers.setdefault("bwd_overlap_group", []).append((g0, g1))
-            else:
-                self._timed("mlp_wgrad_fine", lambda: mlp_wgrad(self.fine, f["acts_f"], dacts_f, f["Pf"], sinks_f))
-                dacts_c = self._timed("mlp_dgrad_coarse",
-                                      lambda: mlp_dgrad(self.coarse, f["pk_c"], f["acts_c"], f["Pc"], g_raw_c))
-                self._timed("mlp_wgrad_coarse", lambda: mlp_wgrad(self.coarse, f["acts_c"], dacts_c, f["Pc"], sinks_c))
-            self.bucket.all_reduce()
-            if optimizer_step:
-                self.step_count += 1
-                call("ctx_adam_step", ptr(self.bucket.flat), ptr(self.bucket.grad), ptr(self.exp_avg),
-                     ptr(self.exp_avg_sq), self.bucket.numel, self.lr, self.betas[0], self.betas[1], self.eps,
-                     self.step_count, 0.0, 1.0 / self.world_size, stream_ptr(dev))
-                self.coarse._packed.invalidate()
-                self.fine._packed.invalidate()
-        return self._loss
-
-    def step_from_host(self, ray_idx_pinned: torch.Tensor, target_pinned: torch.Tensor,
-                       loss_pinned: torch.Tensor) -> "torch.cuda.Event":
-        """End-to-end entry: host (pinned) inputs in, loss back to the host.  Asynchronous: the returned event marks
-        the arrival of the loss in ``loss_pinned``, so a training loop can submit step i+1 before it reads the loss
-        of step i (the launches of the next step then hide behind the GPU work of this one)."""
-        idx = ray_idx_pinned.to(self.device, non_blocking=True)
-        tgt = target_pinned.to(self.device, non_blocking=True)
-        loss = self.step(idx, tgt)
-        loss_pinned.copy_(loss, non_blocking=True)
-        done = torch.cuda.Event()
-        done.record(torch.cuda.current_stream(self.device))
-        return done     # loss_pinned is valid once this event has completed
+                           sphere=sphere, want_viewdirs=True, ray_idx=ray_idx)
+            n = r["rays_o"].shape[0]
+            raw = torch.empty(n * n_samples, 4, device=dev)
+            self._fwd(self.fine, (r["rays_o"], r["rays_d"], r["viewdirs"], r["z_vals"]), n * n_samples, raw, None)
+            rgb, disp, acc, _, depth = self._composite(raw, r["z_vals"], r["rays_d"], n, n_samples)
+        if ray_idx is None:
+            return dict(rgb_map=rgb.reshape(H, W, 3), disp_map=disp.reshape(H, W), acc_map=acc.reshape(H, W),
+                        depth_map=depth.reshape(H, W))
+        return dict(rgb_map=rgb, disp_map=disp, acc_map=acc, depth_map=depth)

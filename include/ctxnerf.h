@@ -50,9 +50,11 @@ int ctx_posenc_bwd(const float* x, const float* g_out, float* g_x, int64_t n, in
 int ctx_raygen_fwd(int H, int W, float fx, float fy, float cx, float cy, const float* c2w,
                    int c2w_ld, const int64_t* ray_idx, int64_t n_rays, int use_ndc,
                    float ndc_focal, float ndc_near, int n_samples, float near, float far,
-                   int lindisp, int perturb, const float* jitter, uint64_t seed, int use_sphere,
-                   const float* sphere, float* rays_o, float* rays_d, float* viewdirs,
-                   float* z_vals, float* near_far, void* stream);
+                   int lindisp, int perturb, const float* jitter, uint64_t seed,
+                   const uint64_t* seed_dev, int use_sphere, const float* sphere, float* rays_o,
+                   float* rays_d, float* viewdirs, float* z_vals, float* near_far, void* stream);
+/* seed_dev (nullable, here and in ctx_resample_fwd): a DEVICE counter added to `seed` inside the kernel, so that a
+ * captured CUDA graph of the training step draws fresh Philox numbers on every replay (ctx_adam_step_dev bumps it). */
 
 /* z_vals [R,S] from per-ray near/far (ray_batch[:,6], ray_batch[:,7] upstream) */
 int ctx_stratified_fwd(const float* near, int64_t near_stride, const float* far,
@@ -91,12 +93,22 @@ int ctx_composite_bwd(const float* raw, const float* z_vals, const float* rays_d
  * z_all (nullable [R,Sm+N]) = sort(cat[z_merge[R,Sm], samples]).               */
 int ctx_resample_fwd(const float* bins, int64_t bins_stride, int mid_bins, const float* weights,
                      int64_t w_stride, const float* cdf_in, const float* u, int det,
-                     uint64_t seed, int64_t R, int B, int N, float* samples, int64_t* inds,
-                     const float* z_merge, int64_t zm_stride, int Sm, float* z_all, void* stream);
+                     uint64_t seed, const uint64_t* seed_dev, int64_t R, int B, int N, float* samples,
+                     int64_t* inds, const float* z_merge, int64_t zm_stride, int Sm, float* z_all,
+                     void* stream);
 /* d samples / d weights -> g_weights [R,B-1] (contiguous) */
 int ctx_resample_bwd(const float* bins, int64_t bins_stride, int mid_bins, const float* weights,
                      int64_t w_stride, const float* u, int det, uint64_t seed, int64_t R, int B,
                      int N, const float* g_samples, float* g_weights, void* stream);
+
+/* Fused training form of raw2outputs (NerfTrainer.step): forward + img2mse(rgb_map, target)
+ * (src/run_nerf_helpers.py:9) + backward in ONE pass over raw.  g_raw [R,S,4] = d loss / d raw with
+ * loss = sum((rgb_map - target)^2) * loss_scale (loss_scale = 1/(3R) for the image mean); loss[0] += that value
+ * (zero it once per step; the coarse and the fine pass add into the same scalar).  weights [R,S] and rgb_map [R,3]
+ * are optional outputs (the coarse pass feeds sample_pdf with its weights).  S <= 512.                        */
+int ctx_composite_train(const float* raw, const float* z_vals, const float* rays_d, const float* noise,
+                        int64_t R, int S, int white_bkgd, const float* target, float loss_scale, float* loss,
+                        float* g_raw, float* weights, float* rgb_map, void* stream);
 
 /* ---- coordinate MLP: NeRF2D, src/run_nerf_helpers.py:68-135 (+ the upstream
  * view-direction head kept as comments :86-95, :117-127) ----------------------
@@ -126,6 +138,12 @@ int ctx_mlp_fwd(const void* net, const void* wpacked, const float* fparams, int 
                 const float* z, int S, int L_pts, int L_dirs, int64_t P, float* out, void* acts,
                 void* stream);
 
+/* same with an SM budget (max_sms > 0: at most that many SMs, 0 = the whole GPU), see ctx_mlp_dgrad_ex */
+int ctx_mlp_fwd_ex(const void* net, const void* wpacked, const float* fparams, int mode, const float* x,
+                   int x_ld, const float* rays_o, const float* rays_d, const float* viewdirs,
+                   const float* z, int S, int L_pts, int L_dirs, int64_t P, float* out, void* acts,
+                   int max_sms, void* stream);
+
 /* Backward of ctx_mlp_fwd w.r.t. the parameters (hand-written dgrad + wgrad
  * tcgen05 kernels; the encoded inputs are data and get no gradient).  g_out
  * [P,out_ch]; acts = records written by ctx_mlp_fwd; dacts = scratch of the same
@@ -133,13 +151,19 @@ int ctx_mlp_fwd(const void* net, const void* wpacked, const float* fparams, int 
  * params; gradients are ACCUMULATED (+=) into them.                              */
 int ctx_mlp_bwd(const void* net, const void* wtpacked, const float* fparams, const float* g_out,
                 const void* acts, void* dacts, int64_t P, float* const* grads, int n_grads,
-                void* stream);
+                const float* const* params, float* scratch, void* stream);
 /* the two halves of ctx_mlp_bwd, separately launchable (and separately timed by bench.py):
  * dgrad fills the dZ records from g_out, wgrad reduces records + dZ records into the gradients. */
 int ctx_mlp_dgrad(const void* net, const void* wtpacked, const float* fparams, const float* g_out,
                   const void* acts, void* dacts, int64_t P, void* stream);
+/* params (HOST array of DEVICE pointers, order of ctx_mlp_pack) and scratch (device,
+ * ctx_mlp_wgrad_scratch_floats() floats, zeroed by the launcher) are read only for a view-direction net: the
+ * feature layer is linear, so its weight gradients and those of views_linears.0[:, :256] are rebuilt from
+ * G = [dZ_views | g_out]^T h and the weights instead of from records of the feature activations (which are never
+ * written).  Both may be NULL for a net without views.                                                        */
+int ctx_mlp_wgrad_scratch_floats(void);
 int ctx_mlp_wgrad(const void* net, const void* acts, const void* dacts, int64_t P, float* const* grads,
-                  int n_grads, void* stream);
+                  int n_grads, const float* const* params, float* scratch, void* stream);
 /* the same with an SM budget (max_sms > 0: at most that many SMs are occupied; 0 = the whole GPU), so that the
  * tensor-bound dgrad of one network can run beside the HBM-bound wgrad of the other on disjoint SM pairs
  * (NerfTrainer.step: dgrad_coarse || wgrad_fine).  dgrad accepts any budget >= 2 (one cluster); wgrad needs two
@@ -147,7 +171,7 @@ int ctx_mlp_wgrad(const void* net, const void* acts, const void* dacts, int64_t 
 int ctx_mlp_dgrad_ex(const void* net, const void* wtpacked, const float* fparams, const float* g_out,
                      const void* acts, void* dacts, int64_t P, int max_sms, void* stream);
 int ctx_mlp_wgrad_ex(const void* net, const void* acts, const void* dacts, int64_t P, float* const* grads,
-                     int n_grads, int max_sms, void* stream);
+                     int n_grads, const float* const* params, float* scratch, int max_sms, void* stream);
 
 /* ---- fused texture map: get_texture_map, src/models/textured_mesh.py:266-301 -----------------------
  * ctx_mlp_fwd mode 2 generates the res x res UV grid (meshgrid of linspace(0,1,res), 'xy' indexing, :269-272),
@@ -182,6 +206,15 @@ int ctx_mse_fwd_bwd(const float* a, const float* b, const float* target, int64_t
 int ctx_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                   float lr, float beta1, float beta2, float eps, int step, float weight_decay,
                   float grad_scale, void* stream);
+
+/* Device-resident step state for a CUDA-graph-captured training step: counters = two
+ * uint64 on the device, [0] Philox seed offset (see seed_dev above), [1] Adam step count.  ctx_step_tick runs first
+ * in a step: counters[0] += 2, counters[1] += 1, loss[0] = 0 (loss nullable).  ctx_adam_step_dev is ctx_adam_step
+ * with the step count read from counters[1].                                                                  */
+int ctx_step_tick(void* counters, float* loss, void* stream);
+int ctx_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      float lr, float beta1, float beta2, float eps, const void* counters, float weight_decay,
+                      float grad_scale, void* stream);
 
 /* diagnostic: one-CTA tcgen05 GEMM C[128,N] = A * B^T (tests pin the descriptor
  * conventions with it); A,B bf16.  mode 0 K-major operands, 1 MN-major.          */

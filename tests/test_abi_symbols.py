@@ -41,8 +41,8 @@ def test_argument_errors_do_not_need_a_gpu(libpath):
     assert lib.ctx_composite_fwd(None, None, None, None, 4, 64, 0, None, None, None, None, None, None) == -1
     assert lib.ctx_composite_fwd(None, None, None, None, 0, 64, 0, None, None, None, None, None, None) == 0
     assert lib.ctx_posenc_fwd(None, None, -1, 3, 10, 1, 1, None) == -1
-    assert lib.ctx_resample_fwd(None, 0, 0, None, 0, None, None, 1, 0, 8, 1, 16, None, None, None, 0, 0, None,
-                                None) == -1
+    assert lib.ctx_resample_fwd(None, 0, 0, None, 0, None, None, 1, 0, None, 8, 1, 16, None, None, None, 0, 0,
+                                None, None) == -1
 
 
 def test_mlp_describe_matches_the_reference_layer_structure(libpath):

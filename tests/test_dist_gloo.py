@@ -91,7 +91,7 @@ def test_reference_arm_of_bench_runs_on_cpu():
     import json
     import subprocess
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0"], capture_output=True, text=True, timeout=600)
+                          "--warmup", "0", "--ref-rays", "256"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "rays/s" and line["value"] > 0

@@ -137,12 +137,12 @@ def test_ndc_bit_exact_and_backward(cuda, golden):
 # --------------------------------------------------------------- composite ---
 def close_w(a, b, what):
     """1e-5 relative with the floor of SURVEY.md H6 (weights reach 1e-10 behind an opaque sample): elementwise
-    for everything above 1 % of the ray's largest value, 1e-7 of that value (+ 2 ulp of 1.0) below.  The oracle's
+    for everything above 0.1 % of the ray's largest value, 1e-8 of that value (+ 2 ulp of 1.0) below.  The oracle's
     cumprod is a sequential fp32 product of up to S factors and the kernel's a blocked one (in-lane serial, warp scan
     across lanes): the two association orders legitimately differ by a few 1e-6 relative on long rays."""
     scale = b.abs().amax(dim=-1, keepdim=True).clamp_min(1e-30) if b.dim() > 1 else b.abs().clamp_min(1e-30)
     err = (a - b).abs()
-    tol = 1e-5 * torch.maximum(b.abs(), scale * 1e-2) + 2.4e-7
+    tol = 1e-5 * torch.maximum(b.abs(), scale * 1e-3) + 2.4e-7
     bad = err > tol
     assert not bad.any(), f"{what}: {int(bad.sum())} elements off, max err {err.max().item():.3e}"
 
@@ -207,7 +207,7 @@ def test_composite_backward(cuda, R, S, white):
     torch.autograd.backward(list(oc), [gs[0].to(cuda), gdisp.to(cuda), gs[2].to(cuda), gs[3].to(cuda), gs[4].to(cuda)])
     a, b = rc.grad.cpu(), r0.grad
     scale = b.abs().amax(dim=(1, 2), keepdim=True).clamp_min(1e-12)
-    assert ((a - b).abs() <= 2e-4 * scale + 1e-6).all(), ((a - b).abs() / scale).max()
+    assert ((a - b).abs() <= 5e-5 * scale + 1e-6).all(), ((a - b).abs() / scale).max()
 
 
 # ---------------------------------------------------------------- resample ---

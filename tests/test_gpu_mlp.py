@@ -248,7 +248,7 @@ def test_trainer_overlapped_backward_equals_sequential(cuda):
         torch.cuda.synchronize()
         grads.append(tr.bucket.grad.clone())
         losses.append(loss.item())
-    assert losses[0] == losses[1]
+    assert abs(losses[0] - losses[1]) <= 1e-6 * abs(losses[0])     # (the loss is an atomic sum over warps)
     ref, got = grads
     assert ref.abs().max().item() > 0
     err = (got - ref).abs().max().item() / ref.abs().max().item()
