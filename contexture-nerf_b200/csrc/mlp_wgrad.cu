@@ -23,14 +23,16 @@ namespace ctx {
 
 // ============================== wgrad ======================================
 // Units of the operand ring are HALF tiles (64 points x channels, <= 32 KB, contiguous in the record);
-// a group = {A half, B half} feeds 4 K16 MMAs per 128-wide M half.  Seven 32 KB slots = three and a half groups: one
-// being consumed, two in flight from HBM, which is what it takes to keep the per-SM share of the HBM
-// bandwidth busy (the kernel is bandwidth-bound: 1 KB per point per layer).
-constexpr int kWgUnitBytes = 32768;
-constexpr int kWgUnits = 7;
+// a group = {A half, B half} feeds 4 K16 MMAs per 128-wide M half.  The ring holds as many GROUP slots of exactly
+// (A bytes + B bytes) as fit into 224 KB (at most kWgMaxGroups): 3 for a 256 x 256 layer job (64 KB per group),
+// 12 for the 18 KB groups of the rgb head.  Small-operand jobs are latency-bound, not bandwidth-bound: with a fixed
+// number of slots they were the stragglers of the whole kernel (the rgb job at ~1.75 groups/us set its duration);
+// with the bytes in flight per SM equalised every job runs at its share of the HBM bandwidth.
+constexpr int kWgRingBytes = 7 * 32768;
+constexpr int kWgMaxGroups = 12;
 constexpr int kWgThreads = 192;     // warp 0 producer, warp 1 MMA, warps 2-5 column sums + flush
 constexpr int kWgMaxJobs = 48;
-constexpr size_t kWgSmemBytes = (size_t)kWgUnits * kWgUnitBytes + 256;
+constexpr size_t kWgSmemBytes = (size_t)kWgRingBytes + 512;
 
 struct WgJob {
   int a_slot, a_ch, a_dz;       // A operand tile: record offset, channels (M, multiple of 128), from dZ records?
@@ -51,13 +53,13 @@ struct WgradArgs {
   int64_t n_tiles;
 };
 struct __align__(8) WgCtl {
-  uint64_t full[kWgUnits], empty[kWgUnits], done;
+  uint64_t full[kWgMaxGroups], empty[kWgMaxGroups], done;
   uint32_t tmem_base;
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const __grid_constant__ WgradArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  WgCtl* ctl = reinterpret_cast<WgCtl*>(smem + kWgUnits * kWgUnitBytes);
+  WgCtl* ctl = reinterpret_cast<WgCtl*>(smem + kWgRingBytes);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // which job does this CTA serve?
   int ji = 0;
@@ -71,9 +73,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const __grid_c
   int64_t my_tiles = 0;
   if (split < a.n_tiles) my_tiles = (a.n_tiles - split + cta_count - 1) / cta_count;
   const int64_t my_groups = 2 * my_tiles;
+  const uint32_t g_bytes = a_bytes + b_bytes;            // one group slot (multiples of 1 KB: channels come in 8s)
+  int n_gs = kWgRingBytes / (int)g_bytes;
+  if (n_gs > kWgMaxGroups) n_gs = kWgMaxGroups;
 
   if (tid == 0) {
-    for (int s = 0; s < kWgUnits; ++s) { tc::mbar_init(&ctl->full[s], 1); tc::mbar_init(&ctl->empty[s], 5); }
+    for (int s = 0; s < kWgMaxGroups; ++s) { tc::mbar_init(&ctl->full[s], 1); tc::mbar_init(&ctl->empty[s], 5); }
     tc::mbar_init(&ctl->done, 1);
     tc::mbar_fence_init();
   }
@@ -87,33 +92,29 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const __grid_c
     const uint8_t* a_src = (J.a_dz ? a.dacts : a.acts) + J.a_slot;
     const uint8_t* b_src = (J.b_dz ? a.dacts : a.acts) + J.b_slot;
     const size_t tile_bytes = a.tile_bytes;
-    uint32_t u = 0;
+    int gs = 0; uint32_t ph = 0;
     for (int64_t gi = 0; gi < my_groups; ++gi) {
       const int64_t tile = split + (gi >> 1) * cta_count;
       const size_t base = (size_t)tile * tile_bytes;
       const int hf = (int)(gi & 1);
-      for (int which = 0; which < 2; ++which, ++u) {
-        const int s = u % kWgUnits;
-        tc::mbar_wait(&ctl->empty[s], ((u / kWgUnits) & 1) ^ 1);
-        if (tc::elect_one()) {
-          const uint8_t* src = which == 0 ? a_src + base + (size_t)hf * J.a_hstride : b_src + base + (size_t)hf * J.b_hstride;
-          const uint32_t bytes = which == 0 ? a_bytes : b_bytes;
-          tc::mbar_arrive_expect_tx(&ctl->full[s], bytes);
-          tc::bulk_g2s(smem + s * kWgUnitBytes, src, bytes, &ctl->full[s]);
-        }
-        __syncwarp();
+      tc::mbar_wait(&ctl->empty[gs], ph ^ 1);
+      if (tc::elect_one()) {
+        uint8_t* dst = smem + (size_t)gs * g_bytes;
+        tc::mbar_arrive_expect_tx(&ctl->full[gs], g_bytes);
+        tc::bulk_g2s(dst, a_src + base + (size_t)hf * J.a_hstride, a_bytes, &ctl->full[gs]);
+        tc::bulk_g2s(dst + a_bytes, b_src + base + (size_t)hf * J.b_hstride, b_bytes, &ctl->full[gs]);
       }
+      __syncwarp();
+      if (++gs == n_gs) { gs = 0; ph ^= 1; }
     }
   } else if (warp == 1) {
     const uint32_t idesc = tc::make_idesc_bf16(128, b_ch, 1, 1);
-    uint32_t u = 0;
-    for (int64_t gi = 0; gi < my_groups; ++gi, u += 2) {
-      const int sa = u % kWgUnits, sb = (u + 1) % kWgUnits;
-      tc::mbar_wait(&ctl->full[sa], (u / kWgUnits) & 1);
-      tc::mbar_wait(&ctl->full[sb], ((u + 1) / kWgUnits) & 1);
+    int gs = 0; uint32_t ph = 0;
+    for (int64_t gi = 0; gi < my_groups; ++gi) {
+      tc::mbar_wait(&ctl->full[gs], ph);
       tc::tc_fence_after();
-      const uint32_t a_base = tc::smem_u32(smem + sa * kWgUnitBytes);
-      const uint32_t b_base = tc::smem_u32(smem + sb * kWgUnitBytes);
+      const uint32_t a_base = tc::smem_u32(smem + (size_t)gs * g_bytes);
+      const uint32_t b_base = a_base + a_bytes;
       if (tc::elect_one()) {
         for (int mh = 0; mh < m_halves; ++mh) {
 #pragma unroll
@@ -124,11 +125,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const __grid_c
             tc::mma_bf16_ss(tmem + mh * 256, da, db, idesc, (gi > 0 || k16 > 0) ? 1u : 0u);
           }
         }
-        tc::mma_commit(&ctl->empty[sa]);
-        tc::mma_commit(&ctl->empty[sb]);
+        tc::mma_commit(&ctl->empty[gs]);
         if (gi == my_groups - 1) tc::mma_commit(&ctl->done);
       }
       __syncwarp();
+      if (++gs == n_gs) { gs = 0; ph ^= 1; }
     }
   } else {
     // ---- column sums of the dZ operand (bias gradients), then the flush ----
@@ -140,14 +141,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const __grid_c
     float s_lo[8], s_hi[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { s_lo[i] = 0.f; s_hi[i] = 0.f; }
-    uint32_t u = 0;
-    for (int64_t gi = 0; gi < my_groups; ++gi, u += 2) {
-      const int sa = u % kWgUnits, sb = (u + 1) % kWgUnits;
-      // always wait for both units: keeps these warps within one ring phase of the MMA issuer
-      tc::mbar_wait(&ctl->full[sa], (u / kWgUnits) & 1);
-      tc::mbar_wait(&ctl->full[sb], ((u + 1) / kWgUnits) & 1);
+    int gs = 0; uint32_t ph = 0;
+    for (int64_t gi = 0; gi < my_groups; ++gi) {
+      // always wait for the group: keeps these warps within one ring phase of the MMA issuer
+      tc::mbar_wait(&ctl->full[gs], ph);
       if (do_bias) {
-        const uint8_t* tile = smem + (bias_from_b ? sb : sa) * kWgUnitBytes;
+        const uint8_t* tile = smem + (size_t)gs * g_bytes + (bias_from_b ? a_bytes : 0u);
 #pragma unroll
         for (int ci = 0; ci < 8; ++ci) {
           const int c = cw + ci * 4;
@@ -162,7 +161,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const __grid_c
         }
       }
       __syncwarp();
-      if (lane == 0) { tc::mbar_arrive(&ctl->empty[sa]); tc::mbar_arrive(&ctl->empty[sb]); }
+      if (lane == 0) tc::mbar_arrive(&ctl->empty[gs]);
+      if (++gs == n_gs) { gs = 0; ph ^= 1; }
     }
     if (do_bias) {
 #pragma unroll

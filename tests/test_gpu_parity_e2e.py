@@ -228,8 +228,11 @@ def test_adam_kernel_matches_torch_adam(cuda):
             torch.cuda.synchronize()
             st = opt.state[ref]
             # (torch computes lerp / addcmul, the kernel b*m + (1-b)*g: a few ulps apart, measured 1.3e-5 relative)
-            torch.testing.assert_close(m, st["exp_avg"], rtol=5e-5, atol=1e-12)
-            torch.testing.assert_close(v, st["exp_avg_sq"], rtol=5e-5, atol=1e-20)
+            # (where b*m and (1-b)*g cancel the relative difference of the sum is unbounded: absolute floor of 1e-7 of
+            #  the gradient scale)
+            gs = float(gr.abs().max()) * scale
+            torch.testing.assert_close(m, st["exp_avg"], rtol=5e-5, atol=1e-7 * gs)
+            torch.testing.assert_close(v, st["exp_avg_sq"], rtol=5e-5, atol=1e-7 * gs * gs)
             # parameters: both subtract an update that agrees to ~1e-5 relative (<= 5e-9 absolute); what is left is
             # the rounding of the result, i.e. a couple of ulps of the parameter
             torch.testing.assert_close(p, ref.detach(), rtol=3e-7, atol=2e-8)
