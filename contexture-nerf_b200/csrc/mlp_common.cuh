@@ -15,8 +15,19 @@ constexpr int kStageBytes = CTX_MLP_W * CTX_MLP_KC * 2;   // 16 KB
 constexpr int kHBytes = kTileM * CTX_MLP_W * 2;            // 64 KB
 constexpr int kXBytes = kTileM * CTX_MLP_XP_PAD * 2;       // 16 KB
 constexpr int kK8Stride = kTileM * 16;                     // 2048 B between 8-wide K chunks of an A tile
-constexpr int kMlpThreads = 352;   // warp 0 producer, warp 1 MMA issuer (tile pair A) / relay, warps 2-9 epilogue,
-                                   // warp 10 MMA issuer (tile pair B)
+// Three warpgroups: warpgroup 0 = control (warp 0 weight producer, warp 1 MMA issuer of tile pair A / peer relay,
+// warp 2 MMA issuer of tile pair B, warp 3 idle), warpgroups 1-2 = the eight epilogue warps.  The roles are
+// warpgroup-aligned so that setmaxnreg can move registers from the control warps (a handful of live values) to the
+// epilogue warps, whose 32-column blocks + record addresses otherwise spill at the 168 registers a 12-warp CTA gets.
+constexpr int kMlpThreads = 384;
+constexpr int kCtlRegs = 56, kEpiRegs = 224;     // 4 x 56 + 8 x 224 = 2016 <= 2048 registers per lane slot
+
+template <int N> __device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N> __device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
 constexpr int kEpiThreadsPerTile = 128;
 
 struct MlpFwdArgs {
@@ -73,10 +84,14 @@ __device__ __forceinline__ void store_row8(uint8_t* tile, int row, int ch0, cons
     q.x = pack_bf16x2(v[0], v[1]); q.y = pack_bf16x2(v[2], v[3]);
     q.z = pack_bf16x2(v[4], v[5]); q.w = pack_bf16x2(v[6], v[7]);
   }
+#ifndef CTX_X_NO_STS      // (timing experiments only: tools/build_variants.sh)
   if (tile) *reinterpret_cast<uint4*>(tile + (ch0 >> 3) * kK8Stride + (row >> 3) * 128 + (row & 7) * 16) = q;
+#endif
+#ifndef CTX_X_NO_STG
   if (gtile)   // streaming store: the record is next read by another kernel, keep it out of the (small) L1
     __stcs(reinterpret_cast<uint4*>(gtile + (row >> 6) * (gC * 128) + (ch0 >> 3) * 1024 + ((row & 63) >> 3) * 128 +
                                     (row & 7) * 16), q);
+#endif
 }
 
 }  // namespace ctx

@@ -72,7 +72,10 @@ mlp_dgrad_kernel(const __grid_constant__ DgradArgs a) {
   tc::cluster_sync_all();
   tc::tc_fence_after();
   const uint32_t tmem = ctl->tmem_base;
-
+  // registers: from the control warpgroup to the two epilogue warpgroups (every warp of a warpgroup executes its call)
+  // (the calls sit INSIDE the role branches: ptxas budgets each region by the setmaxnreg that dominates it)
+  if (warp < 4) {
+  reg_dealloc<kCtlRegs>();
   if (warp == 0) {
     // ============ transposed-weight producer (this CTA's half of every chunk, twice per step) ============
     uint32_t g = 0;
@@ -95,7 +98,7 @@ mlp_dgrad_kernel(const __grid_constant__ DgradArgs a) {
         }
       }
     }
-  } else if (warp == 1 || warp == 10) {
+  } else if (warp == 1 || warp == 2) {
     if (r != 0) {
       if (warp == 1) {
       // ============ peer CTA: relay "my half landed" to the leader, once per chunk pair ============
@@ -114,7 +117,7 @@ mlp_dgrad_kernel(const __grid_constant__ DgradArgs a) {
         }
       }
     } else {
-      // ============ leader CTA: two MMA issuers, warp 1 -> tile pair A, warp 10 -> tile pair B ============
+      // ============ leader CTA: two MMA issuers, warp 1 -> tile pair A, warp 2 -> tile pair B ============
       // (one thread cannot issue fast enough to keep the tensor pipe fed; see mlp_fwd.cu)
       const int ph = warp == 1 ? 0 : 1;
       if (tc::elect_one()) {
@@ -161,10 +164,12 @@ mlp_dgrad_kernel(const __grid_constant__ DgradArgs a) {
       }
       __syncwarp();
     }
-  } else if (warp >= 2 && warp <= 9) {
+  }
+  } else {
+    reg_alloc<kEpiRegs>();
     // ============ head-init + epilogue warps ============
     const int q = warp & 3;                 // TMEM lane quarter
-    const int hi = (warp - 2) >> 2;         // epilogue: column half ; head init: tile (0 = A, 1 = B)
+    const int hi = (warp - 4) >> 2;         // epilogue: column half ; head init: tile (0 = A, 1 = B)
     const int row = q * 32 + lane;
     const float* hw = s_head;
     const bool has_views = net.in_views > 0;

@@ -76,7 +76,7 @@ __device__ __forceinline__ void encode_row2(uint8_t* tile, int row, const float*
 
 // Diagnostics: spin on an mbarrier; when a (pinned, host-visible) buffer is supplied a waiter that has been
 // stuck for ~0.2 s records {tag, block, warp, info, parity} there and traps, so a deadlock names its waiters.
-__device__ __noinline__ void hang_report(unsigned long long* buf, uint32_t tag, uint32_t info, uint32_t parity) {
+__device__ __forceinline__ void hang_report(unsigned long long* buf, uint32_t tag, uint32_t info, uint32_t parity) {
   const unsigned long long i = atomicAdd(buf, 1ull);
   if (i < 60) {
     unsigned long long* e = buf + 8 + i * 4;
@@ -143,7 +143,10 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
   tc::cluster_sync_all();
   tc::tc_fence_after();
   const uint32_t tmem = ctl->tmem_base;
-
+  // registers: from the control warpgroup to the two epilogue warpgroups (every warp of a warpgroup executes its call)
+  // (the calls sit INSIDE the role branches: ptxas budgets each region by the setmaxnreg that dominates it)
+  if (warp < 4) {
+  reg_dealloc<kCtlRegs>();
   if (warp == 0) {
     // ============ weight-stream producer: this CTA's half of every chunk, twice per layer ============
     // chunks are staged in pairs: one expect_tx / full barrier covers two consecutive 8 KB stages
@@ -177,7 +180,7 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
         }
       }
     }
-  } else if (warp == 1 || warp == 10) {
+  } else if (warp == 1 || warp == 2) {
     {
       if (r != 0) {
         if (warp == 1) {
@@ -197,7 +200,7 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
           }
         }
       } else {
-        // ============ leader CTA: two MMA issuers, warp 1 -> tile pair A, warp 10 -> tile pair B ============
+        // ============ leader CTA: two MMA issuers, warp 1 -> tile pair A, warp 2 -> tile pair B ============
         // Issuing is single-thread work (~400 cycles of dependent instructions per chunk: barrier polls,
         // descriptor builds, vector->uniform register moves); one thread cannot keep a 128-cycle-per-MMA
         // pipe fed, two threads working on alternate phases can.  Phases are padded to whole chunk pairs so
@@ -241,10 +244,12 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
                 // other issuer (the first 4 pairs of a layer phase): until that use has been consumed the full
                 // barrier still sits in the older phase and a wait for this one would pass spuriously, so make sure
                 // of it first (own pairs need no check: this thread saw their phase complete before issuing).
+                const long long f0 = PCLK();
                 if (c < kStages2 && g >= kStages2)
                   mbar_wait_dbg<kProf>(empty0 + (s >> 1) * 8, ((g - kStages2) / kStages2) & 1, a.hang, 6 + ph * 10,
                                 (uint32_t)(l * 1000 + g % 1000));
                 mbar_wait_dbg<kProf>(full0 + (s >> 1) * 8, (g / kStages2) & 1, a.hang, 4 + ph * 10, (uint32_t)(l * 1000 + g % 1000));   // both halves landed (peer relays)
+                t_full += PCLK() - f0;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                   const int cc = c + j;
@@ -267,14 +272,16 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
         if (kProf && a.prof && lane == 0) {
           unsigned long long* pp = a.prof + blockIdx.x * 16 + (ph ? 0 : 2);
           if (ph == 0) { pp[0] = t_act; pp[1] = t_full; pp[2] = t_peer; pp[7] = t_issue; pp[3] = PCLK() - t_begin; }
-          else { pp[0] = t_act; pp[1] = t_issue; }
+          else { pp[0] = t_act; pp[1] = t_full; }
         }
       }
     }
-  } else if (warp >= 2 && warp <= 9) {
+  }
+  } else {
+    reg_alloc<kEpiRegs>();
     // ============ encode + epilogue warps ============
     const int q = warp & 3;                 // TMEM lane quarter
-    const int hi = (warp - 2) >> 2;         // epilogue: column half ; encode: tile (0 = A, 1 = B)
+    const int hi = (warp - 4) >> 2;         // epilogue: column half ; encode: tile (0 = A, 1 = B)
     const int row = q * 32 + lane;
     // head weights: shared memory for the view-direction net, global (L2) for the 4 x 256 output_linear
     const float* hw = net.in_views > 0 ? s_head : a.fparams + net.head_off;
@@ -369,6 +376,7 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
             constexpr bool FINAL = (EPI == CTX_EPI_FINAL_VIEWS || EPI == CTX_EPI_FINAL_OUT);
             uint8_t* const grec = (kRec && Lact >= 0) ? rec + Lact : nullptr;   // (feature layer: no record)
             auto process = [&](const uint32_t (&vr)[32], int cb) {
+#ifndef CTX_X_NO_MASK
               if constexpr (kRec && RELU) {
                 // bit (31-j) = sign of pre-activation j (the ReLU mask the dgrad kernel reads); four independent
                 // shift chains instead of one 32-deep dependent one
@@ -383,6 +391,7 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
                 const uint32_t neg = (n0 << 24) | (n1 << 16) | (n2 << 8) | n3;
                                 __stcs(reinterpret_cast<uint32_t*>(rec + Lmask) + cb * kTileM + row, neg);   // [column block][row]: coalesced
               }
+#endif
               float v[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(vr[j]);

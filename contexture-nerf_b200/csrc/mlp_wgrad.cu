@@ -245,45 +245,79 @@ __global__ void __launch_bounds__(kWgThreads, 1) mlp_wgrad_kernel(const __grid_c
 constexpr int kPostGtFloats = 144 * 256, kPostScratchFloats = 144 * 256 + 144;
 __device__ __forceinline__ float bf16r(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 
-__global__ void wgrad_post_kernel(const float* __restrict__ scratch, const float* __restrict__ W_f,
-                                  const float* __restrict__ b_f, const float* __restrict__ W_v, int ld_v,
-                                  float* __restrict__ gW_f, float* __restrict__ gb_f, float* __restrict__ gW_v,
-                                  float* __restrict__ gb_v, float* __restrict__ gw_alpha, float* __restrict__ gb_alpha) {
+// One 256-thread block per 32 x 32 output tile (shared-memory tiles, K swept in steps of 32):
+//   blocks [0, 64)   : dW_f[f][m]  (256 x 256, K = v over 128)     A = W_vh^T (read [v][f]), B = Gt [v][m]
+//   blocks [64, 96)  : dW_vh[v][f] (128 x 256, K = m over 256)     A = Gt [v][m],            B = W_f^T (read [f][m])
+//   block 96         : alpha head + the three bias vectors
+__global__ void __launch_bounds__(256) wgrad_post_kernel(
+    const float* __restrict__ scratch, const float* __restrict__ W_f, const float* __restrict__ b_f,
+    const float* __restrict__ W_v, int ld_v, float* __restrict__ gW_f, float* __restrict__ gb_f,
+    float* __restrict__ gW_v, float* __restrict__ gb_v, float* __restrict__ gw_alpha, float* __restrict__ gb_alpha) {
   const float* Gt = scratch;
   const float* sv = scratch + kPostGtFloats;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < 256 * 256) {                       // dW_f[f][m] += sum_v W_vh[v][f] Gt[v][m]
-    const int f = t >> 8, m = t & 255;
-    float acc = 0.f;
-#pragma unroll 8
-    for (int v = 0; v < 128; ++v) acc = fmaf(bf16r(__ldg(W_v + v * ld_v + f)), Gt[v * 256 + m], acc);
-    gW_f[t] += acc;
-    if (m == 0) {
-      float b = 0.f;
-      for (int v = 0; v < 128; ++v) b = fmaf(bf16r(__ldg(W_v + v * ld_v + f)), sv[v], b);
-      gb_f[f] += b;
+  __shared__ float sA[32][33], sB[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8 threads, 4 outputs each (rows ty, ty+8, ...)
+  const int blk = blockIdx.x;
+  if (blk < 64) {
+    const int f0 = (blk >> 3) * 32, m0 = (blk & 7) * 32;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int v0 = 0; v0 < 128; v0 += 32) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int v = v0 + ty + 8 * r;
+        sA[ty + 8 * r][tx] = bf16r(__ldg(W_v + v * ld_v + f0 + tx));   // [v][f]
+        sB[ty + 8 * r][tx] = Gt[v * 256 + m0 + tx];                    // [v][m]
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const float b = sB[k][tx];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] = fmaf(sA[k][ty + 8 * r], b, acc[r]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) gW_f[(f0 + ty + 8 * r) * 256 + m0 + tx] += acc[r];
+    return;
+  }
+  if (blk < 96) {
+    const int t = blk - 64;
+    const int v0 = (t >> 3) * 32, f0 = (t & 7) * 32;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int m0 = 0; m0 < 256; m0 += 32) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        sA[ty + 8 * r][tx] = Gt[(v0 + ty + 8 * r) * 256 + m0 + tx];               // [v][m]
+        sB[ty + 8 * r][tx] = bf16r(__ldg(W_f + (f0 + ty + 8 * r) * 256 + m0 + tx));   // [f][m]
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 32; ++k) {
+        const float b = sB[tx][k];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] = fmaf(sA[ty + 8 * r][k], b, acc[r]);
+      }
+      __syncthreads();
+    }
+    const float bf = bf16r(b_f[f0 + tx]);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int v = v0 + ty + 8 * r;
+      gW_v[v * ld_v + f0 + tx] += acc[r] + sv[v] * bf;
     }
     return;
   }
-  const int u = t - 256 * 256;
-  if (u < 128 * 256) {                       // dW_vh[v][f] += sum_m Gt[v][m] W_f[f][m] + s_v[v] b_f[f]
-    const int v = u >> 8, f = u & 255;
-    float acc = sv[v] * bf16r(b_f[f]);
-    const float4* wrow = reinterpret_cast<const float4*>(W_f + f * 256);
-    const float4* grow = reinterpret_cast<const float4*>(Gt + v * 256);
-#pragma unroll 4
-    for (int m4 = 0; m4 < 64; ++m4) {
-      const float4 w = __ldg(wrow + m4), g = grow[m4];
-      acc = fmaf(g.x, bf16r(w.x), acc); acc = fmaf(g.y, bf16r(w.y), acc);
-      acc = fmaf(g.z, bf16r(w.z), acc); acc = fmaf(g.w, bf16r(w.w), acc);
-    }
-    gW_v[v * ld_v + f] += acc;
-    if (f == 0) gb_v[v] += sv[v];
-    return;
+  // heads and biases
+  const int i = threadIdx.x;
+  gw_alpha[i] += Gt[(128 + 3) * 256 + i];
+  if (i == 0) gb_alpha[0] += sv[128 + 3];
+  if (i < 128) gb_v[i] += sv[i];
+  {
+    float b = 0.f;                                            // db_f[f] = sum_v W_vh[v][f] s_v
+    for (int v = 0; v < 128; ++v) b = fmaf(bf16r(__ldg(W_v + v * ld_v + i)), sv[v], b);
+    gb_f[i] += b;
   }
-  const int a = u - 128 * 256;
-  if (a < 256) gw_alpha[a] += Gt[(128 + 3) * 256 + a];
-  if (a == 0) gb_alpha[0] += sv[128 + 3];
 }
 
 }  // namespace ctx
@@ -425,9 +459,8 @@ extern "C" int ctx_mlp_wgrad_ex(const void* net_host, const void* acts, const vo
     if (e != cudaSuccess) return (int)e;
   }
   if (views) {
-    const int n_out = 256 * 256 + 128 * 256 + 256;
     const int ld_v = 256 + net.in_views;
-    ctx::wgrad_post_kernel<<<(n_out + 255) / 256, 256, 0, st>>>(scratch, params[2 * D], params[2 * D + 1],
+    ctx::wgrad_post_kernel<<<97, 256, 0, st>>>(scratch, params[2 * D], params[2 * D + 1],
                                                                 params[2 * D + 4], ld_v, grads[2 * D], grads[2 * D + 1],
                                                                 grads[2 * D + 4], grads[2 * D + 5], grads[2 * D + 2],
                                                                 grads[2 * D + 3]);

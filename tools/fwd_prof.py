@@ -10,7 +10,7 @@ R, S = 4096, 192
 o = torch.randn(R, 3, device=dev); d = torch.randn(R, 3, device=dev); d = d / d.norm(dim=-1, keepdim=True)
 z = torch.sort(torch.rand(R, S, device=dev) * 4 + 2, -1)[0]
 prof = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
-names = {14: "epi2.wait_rec", 15: "epi2.consume", 1: "epi2.emit", 2: "mma.wait_act", 3: "mma.wait_full", 4: "mma.wait_peer", 9: "mma.issue", 5: "mma.total",
+names = {0: "mmaB.wait_act", 1: "mmaB.wait_full", 2: "mma.wait_act", 3: "mma.wait_full", 4: "mma.wait_peer", 9: "mma.issue", 5: "mma.total",
          6: "epi2.wait_acc", 7: "epi2.body", 8: "epi2.total", 13: "epi2.encode", 10: "epi9.wait_acc", 11: "epi9.body", 12: "epi9.total"}
 hang = torch.zeros(8 + 64 * 4, dtype=torch.int64).pin_memory()
 _lib.lib().ctx_mlp_set_hang_buffer(hang.data_ptr())
