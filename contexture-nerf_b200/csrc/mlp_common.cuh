@@ -6,7 +6,18 @@
 #include "tc_common.cuh"
 #include "mlp_desc.h"
 
+#include <cuda.h>     // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no -lcuda)
+
 namespace ctx {
+
+// Tensor map over a record buffer for the epilogues' tile stores: a [128 points x 256 channels] bf16 tile sits in
+// shared memory as [k8 = 32][half = 2][64 rows x 16 B] (the K-major A-operand image) and in the record as two
+// 64-point halves of [k8][64 rows x 16 B]; with 8-byte elements that is the 4-D box {128, 2, 32, 1} of the tensor
+//   dim0: 128 x u64 (1 KB, contiguous) | dim1: half, stride 32 KB | dim2: 1 KB units of a tile's record, stride 1 KB
+//   | dim3: tile, stride tile_bytes
+// so ONE cp.async.bulk.tensor moves a whole tile-layer (64 KB) into both halves of a 256-channel slot
+// (coordinates {0, 0, slot_offset / 1024, tile}).  Returns 0 on success.
+int make_record_tensor_map(CUtensorMap* out, void* base, int tile_bytes, int64_t n_tiles);
 
 
 constexpr int kTileM = 128;
@@ -20,7 +31,7 @@ constexpr int kK8Stride = kTileM * 16;                     // 2048 B between 8-w
 // warpgroup-aligned so that setmaxnreg can move registers from the control warps (a handful of live values) to the
 // epilogue warps, whose 32-column blocks + record addresses otherwise spill at the 168 registers a 12-warp CTA gets.
 constexpr int kMlpThreads = 384;
-constexpr int kCtlRegs = 56, kEpiRegs = 224;     // 4 x 56 + 8 x 224 = 2016 <= 2048 registers per lane slot
+constexpr int kCtlRegs = 56, kEpiRegs = 224;     // per scheduler: (56 + 2 x 224) x 32 = 16 128 <= 16 384 registers
 
 template <int N> __device__ __forceinline__ void reg_dealloc() {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
@@ -45,6 +56,8 @@ struct MlpFwdArgs {
   unsigned long long* prof; // nullable: per-CTA cycle counters (diagnostics), 16 per CTA
   unsigned long long* hang; // nullable: host-visible buffer for the deadlock reporter (diagnostics)
   int debug;                // diagnostics: 1 = epilogue skips TMEM loads/stores, 2 = issuer skips the MMAs
+  int use_tma;              // training: 256-wide activation tiles leave through one tensor-map TMA store each
+  CUtensorMap tmap;         // over the activation record buffer (make_record_tensor_map)
 };
 
 

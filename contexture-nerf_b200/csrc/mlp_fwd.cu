@@ -30,6 +30,8 @@
 // Reference semantics: NeRF2D.forward, /root/reference/src/run_nerf_helpers.py:106-135
 // (+ commented view branch :117-127); Embedder.embed :44-45.
 #include "mlp_common.cuh"
+#include <stdlib.h>
+#include <string.h>
 
 namespace ctx {
 
@@ -41,6 +43,7 @@ constexpr int kStage2Bytes = kStageBytes / 2;   // 8 KB half-chunk
 struct __align__(8) Mlp2SmemCtl {
   uint64_t full[kPairs2], empty[kPairs2];
   uint64_t acc_full[kTiles], act_ready[kTiles];
+  uint64_t rec_ready[kTiles], rec_free[kTiles];   // epilogue -> store warp: tile written ; store warp -> epilogue: read
   uint32_t tmem_base;
 };
 constexpr size_t kMlp2SmemBytes = (size_t)kTiles * (kHBytes + kXBytes) + (size_t)kStages2 * kStage2Bytes +
@@ -131,7 +134,10 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
       // leader: its own producer's arrive + the peer's relay ("my half landed too")
       tc::mbar_init(&ctl->full[s], r == 0 ? 2 : 1); tc::mbar_init(&ctl->empty[s], 1);
     }
-    for (int t = 0; t < kTiles; ++t) { tc::mbar_init(&ctl->acc_full[t], 1); tc::mbar_init(&ctl->act_ready[t], 16); }
+    for (int t = 0; t < kTiles; ++t) {
+      tc::mbar_init(&ctl->acc_full[t], 1); tc::mbar_init(&ctl->act_ready[t], 16);
+      tc::mbar_init(&ctl->rec_ready[t], 8); tc::mbar_init(&ctl->rec_free[t], 1);
+    }
     tc::mbar_fence_init();
   }
   if (warp == 1) tc::tmem_alloc2(&ctl->tmem_base, 512);
@@ -276,6 +282,33 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
         }
       }
     }
+  } else if (warp == 3 && kRec && a.use_tma) {
+    // ============ record-store warp (training): one TMA tensor store per finished 256-wide activation tile ============
+    // The epilogue leaves the tile in shared memory anyway (next layer's A operand); this warp ships the same bytes
+    // to the activation record with ONE instruction, so the epilogue warps issue no global stores for it.
+    uint32_t n_st = 0;
+    for (int64_t it = cid; it < n_citers; it += ncl) {
+      for (int l = 0; l < net.n_layers; ++l) {
+        const int Lact = net.L[l].act_slot;
+        if (Lact < 0 || net.L[l].rec_ch != CTX_MLP_W || net.L[l].epi == CTX_EPI_FINAL_VIEWS ||
+            net.L[l].epi == CTX_EPI_FINAL_OUT)
+          continue;
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+          tc::mbar_wait(&ctl->rec_ready[ph], n_st & 1);
+          if (tc::elect_one()) {
+            tc::tma_store_4d(&a.tmap, h_buf + ph * kHBytes, 0, 0, Lact >> 10, (int)(it * 4 + ph * 2 + r));
+            tc::bulk_commit();
+            tc::bulk_wait_read<0>();          // the tile may be overwritten once the copy has read it
+            tc::mbar_arrive(&ctl->rec_free[ph]);
+          }
+          __syncwarp();
+        }
+        ++n_st;
+      }
+    }
+    if (tc::elect_one()) tc::bulk_wait<0>();
+    __syncwarp();
   }
   } else {
     reg_alloc<kEpiRegs>();
@@ -293,14 +326,22 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
     long long t_acc = 0, t_body = 0, t_enc = 0;
     const long long t_begin = PCLK();
 
-    auto arrive_act = [&](int ph) {
+    const bool use_tma = kRec && a.use_tma != 0;
+    uint32_t n_st0 = 0, n_st1 = 0;          // TMA stores issued so far from each tile buffer
+    auto arrive_act = [&](int ph, bool rec = false) {
       tc::fence_proxy_async_smem();
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
+        if (rec) tc::mbar_arrive(&ctl->rec_ready[ph]);
         if (r == 0) tc::mbar_arrive(&ctl->act_ready[ph]);
         else tc::mbar_arrive_remote(&ctl->act_ready[ph], 0);
       }
+    };
+    // before (re)writing a tile's h buffer: the last TMA store issued from it must have finished reading it
+    auto wait_tile_free = [&](int ph) {
+      const uint32_t n = ph ? n_st1 : n_st0;
+      if (n > 0) tc::mbar_wait(&ctl->rec_free[ph], (n - 1) & 1);
     };
     auto encode_tile = [&](int64_t it, int te) {   // encode rows of tile `te` for cluster iteration `it`
       const int64_t tile_idx = it * 4 + te * 2 + r;
@@ -366,6 +407,8 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
           acc_phase[ph] ^= 1;
           tc::tc_fence_after();
           float head[4] = {0.f, 0.f, 0.f, 0.f};
+          const bool tma_rec = use_tma && !is_final && Lact >= 0 && Lrec == CTX_MLP_W;
+          if (kRec && !is_final) wait_tile_free(ph);
           // The bias is already inside the accumulator (constant-1 channel x bias row of the weight stream),
           // so a hidden-layer epilogue is: TMEM load -> (training: sign mask) -> relu+bf16 pack -> store.
           // One straight-line instantiation per (epilogue kind, relu): the per-block path of a plain hidden
@@ -374,7 +417,8 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
             constexpr int EPI = decltype(epi_c)::value;
             constexpr bool RELU = decltype(relu_c)::value;
             constexpr bool FINAL = (EPI == CTX_EPI_FINAL_VIEWS || EPI == CTX_EPI_FINAL_OUT);
-            uint8_t* const grec = (kRec && Lact >= 0) ? rec + Lact : nullptr;   // (feature layer: no record)
+            // (feature layer: no record; tma_rec: the tile leaves through the store warp)
+            uint8_t* const grec = (kRec && Lact >= 0 && !tma_rec) ? rec + Lact : nullptr;
             auto process = [&](const uint32_t (&vr)[32], int cb) {
 #ifndef CTX_X_NO_MASK
               if constexpr (kRec && RELU) {
@@ -423,14 +467,29 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
                   store_row8(FINAL ? nullptr : my_h, row, cb * 32 + j, v + j, RELU, grec, Lrec);
               }
             };
-            uint32_t va[32];
             const int cb0 = hi * ncb;
-            // (loads are NOT run ahead of the processing: measured slower, with either one or two in flight)
+#ifndef CTX_X_PIPE_LD
+            // (loads are NOT run ahead of the processing: measured slower in this kernel, before and after the
+            //  epilogue warps got 224 registers; the dgrad epilogue does profit from it)
+            uint32_t va[32];
             for (int cbi = 0; cbi < ncb; ++cbi) {
               tc::tmem_ld32(my_acc + (cb0 + cbi) * 32, va);
               tc::tmem_wait_ld(va);
               process(va, cb0 + cbi);
             }
+#else
+            uint32_t va[32], vb[32];
+            tc::tmem_ld32(my_acc + cb0 * 32, va);
+            tc::tmem_wait_ld(va);
+            for (int cbi = 0; cbi < ncb; cbi += 2) {
+              tc::tmem_ld32(my_acc + (cb0 + cbi + 1) * 32, vb);
+              process(va, cb0 + cbi);
+              tc::tmem_wait_ld(vb);
+              if (cbi + 2 < ncb) tc::tmem_ld32(my_acc + (cb0 + cbi + 2) * 32, va);
+              process(vb, cb0 + cbi + 1);
+              if (cbi + 2 < ncb) tc::tmem_wait_ld(va);
+            }
+#endif
           };
           if (!(dbg & 1)) {
             using std::integral_constant;
@@ -496,7 +555,8 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
             t_enc += PCLK() - e2;
             if (nit < n_citers) arrive_act(ph);
           } else {
-            arrive_act(ph);
+            arrive_act(ph, tma_rec);
+            if (tma_rec) { if (ph) ++n_st1; else ++n_st0; }
           }
           t_body += PCLK() - e1;
         }
@@ -552,6 +612,15 @@ extern "C" int ctx_mlp_fwd_ex(const void* net_host, const void* wpacked, const f
   a.wpacked = (const uint8_t*)wpacked; a.fparams = fparams; a.mode = mode; a.x = x; a.x_ld = x_ld;
   a.rays_o = rays_o; a.rays_d = rays_d; a.viewdirs = viewdirs; a.z = z; a.S = S; a.L_pts = L_pts;
   a.L_dirs = L_dirs; a.P = P; a.out = out; a.acts = (uint8_t*)acts;
+  a.use_tma = 0;
+  memset(&a.tmap, 0, sizeof(a.tmap));
+  if (a.acts) {
+    // activation tiles can go out by TMA tensor stores (CTXNERF_FWD_TMA=1; default off: measured slower than the
+    // register stores in this kernel, unlike in dgrad -- profiles/README.md r02)
+    static const bool want = [] { const char* e = getenv("CTXNERF_FWD_TMA"); return e && e[0] == '1'; }();
+    const int64_t n_tiles = 4 * ctx::ceil_div(P, (int64_t)ctx::kTileM * 4);
+    a.use_tma = want && ctx::make_record_tensor_map(&a.tmap, a.acts, a.net.act_tile_bytes, n_tiles) == 0;
+  }
   a.prof = (unsigned long long*)ctx_mlp_prof_buffer; a.debug = ctx_mlp_debug_flags;
   a.hang = (unsigned long long*)ctx_mlp_hang_buffer;
   cudaStream_t st = (cudaStream_t)stream;

@@ -109,6 +109,33 @@ __global__ void mlp_pack_kernel(const __grid_constant__ PackArgs a) {
 
 }  // namespace ctx
 
+#include <cuda.h>
+namespace ctx {
+int make_record_tensor_map(CUtensorMap* out, void* base, int tile_bytes, int64_t n_tiles) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+        qres != cudaDriverEntryPointSuccess)
+      return CTX_ERR_UNSUPPORTED;
+    encode = (EncodeFn)fn;
+  }
+  if (tile_bytes % 1024 != 0 || n_tiles < 1 || (reinterpret_cast<uintptr_t>(base) & 15) != 0) return CTX_ERR_BAD_ARG;
+  const cuuint64_t gdim[4] = {128, 2, (cuuint64_t)(tile_bytes / 1024), (cuuint64_t)n_tiles};
+  const cuuint64_t gstride[3] = {32768, 1024, (cuuint64_t)tile_bytes};      // bytes, dims 1..3
+  const cuuint32_t box[4] = {128, 2, 32, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult rc = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, base, gdim, gstride, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return rc == CUDA_SUCCESS ? 0 : CTX_ERR_UNSUPPORTED;
+}
+}  // namespace ctx
+
 extern "C" int ctx_mlp_net_bytes(void) { return (int)sizeof(CtxMlpNet); }
 
 extern "C" int ctx_mlp_describe(int D, uint32_t skip_mask, int in_pts, int in_views, int out_ch, void* net_out) {
