@@ -580,13 +580,21 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
 
 }  // namespace ctx
 
-// diagnostics: if set (device pointer, 16 x uint64 per CTA), the 2-CTA kernels record where their roles wait
+// Diagnostics live in libctxnerf_diag.so only (built with -DCTXNERF_DIAG, include/ctxnerf_diag.h): if set (device
+// pointer, 16 x uint64 per CTA), the profiling instantiation of the kernel records where its roles wait.  The product
+// library carries neither the hooks nor the profiling kernels.
+#ifdef CTXNERF_DIAG
 static void* ctx_mlp_prof_buffer = nullptr;
 static int ctx_mlp_debug_flags = 0;
 static void* ctx_mlp_hang_buffer = nullptr;
 extern "C" int ctx_mlp_set_hang_buffer(void* p) { ctx_mlp_hang_buffer = p; return 0; }
 extern "C" int ctx_mlp_set_debug(int f) { ctx_mlp_debug_flags = f; return 0; }
 extern "C" int ctx_mlp_set_prof_buffer(void* p) { ctx_mlp_prof_buffer = p; return 0; }
+#else
+static void* const ctx_mlp_prof_buffer = nullptr;
+static const int ctx_mlp_debug_flags = 0;
+static void* const ctx_mlp_hang_buffer = nullptr;
+#endif
 
 extern "C" int ctx_mlp_fwd_ex(const void* net_host, const void* wpacked, const float* fparams, int mode,
                                const float* x, int x_ld, const float* rays_o, const float* rays_d,
@@ -625,8 +633,12 @@ extern "C" int ctx_mlp_fwd_ex(const void* net_host, const void* wpacked, const f
   a.hang = (unsigned long long*)ctx_mlp_hang_buffer;
   cudaStream_t st = (cudaStream_t)stream;
   using KernelFn = void (*)(ctx::MlpFwdArgs);
+#ifdef CTXNERF_DIAG
   static const KernelFn kernels[4] = {ctx::mlp_fwd_kernel<false, false>, ctx::mlp_fwd_kernel<false, true>,
                                       ctx::mlp_fwd_kernel<true, false>, ctx::mlp_fwd_kernel<true, true>};
+#else
+  static const KernelFn kernels[2] = {ctx::mlp_fwd_kernel<false, false>, ctx::mlp_fwd_kernel<false, true>};
+#endif
   static ctx::DeviceOnce attr_once;
   if (attr_once.needed()) {
     for (KernelFn k : kernels) {

@@ -40,9 +40,6 @@ _SIGNATURES = {
     "ctx_mlp_pack": (c_int, [P, P, c_int, P, P, P, P]),
     "ctx_mlp_fwd": (c_int, [P, P, P, c_int, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int64, P, P, P]),
     "ctx_mlp_fwd_ex": (c_int, [P, P, P, c_int, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int64, P, P, c_int, P]),
-    "ctx_mlp_set_prof_buffer": (c_int, [P]),
-    "ctx_mlp_set_debug": (c_int, [c_int]),
-    "ctx_mlp_set_hang_buffer": (c_int, [P]),
     "ctx_mlp_dgrad": (c_int, [P, P, P, P, P, P, c_int64, P]),
     "ctx_mlp_wgrad": (c_int, [P, P, P, c_int64, P, c_int, P, P, P]),
     "ctx_mlp_bwd": (c_int, [P, P, P, P, P, P, c_int64, P, c_int, P, P, P]),
@@ -58,15 +55,40 @@ _SIGNATURES = {
     "ctx_step_tick": (c_int, [P, P, P]),
     "ctx_adam_step_dev": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, P, c_float, c_float, P]),
     "ctx_mse_fwd_bwd": (c_int, [P, P, P, c_int64, c_float, P, P, P, P]),
+}
+
+
+# diagnostics build (libctxnerf_diag.so, include/ctxnerf_diag.h): tools/ and one GPU test only
+_DIAG_SIGNATURES = {
+    "ctx_mlp_set_prof_buffer": (c_int, [P]),
+    "ctx_mlp_set_debug": (c_int, [c_int]),
+    "ctx_mlp_set_hang_buffer": (c_int, [P]),
     "ctx_tcgen05_selftest": (c_int, [P, P, P, c_int, c_int, c_int, c_int, P]),
     "ctx_tcgen05_mma_rate": (c_int, [c_int, c_int, c_int, c_int, P, c_int, P, P]),
     "ctx_tcgen05_sync_cost": (c_int, [P, c_int, P]),
     "ctx_tcgen05_selftest2": (c_int, [P, P, P, c_int, c_int, P]),
 }
+DIAG_LIB_PATH = os.path.join(_HERE, "libctxnerf_diag.so")
 
 
 class CtxNerfError(RuntimeError):
     pass
+
+
+def use_diag_lib() -> ctypes.CDLL:
+    """Switch this process to the diagnostics build (call before the first kernel launch): the same entry points
+    plus the profiling / micro-benchmark hooks of include/ctxnerf_diag.h."""
+    global _lib, LIB_PATH
+    if not os.path.exists(DIAG_LIB_PATH):
+        raise CtxNerfError(f"{DIAG_LIB_PATH} not found: python contexture-nerf_b200/ctxnerf/build.py --diag")
+    LIB_PATH = DIAG_LIB_PATH
+    _lib = None
+    handle = lib()
+    for name, (res, args) in _DIAG_SIGNATURES.items():
+        fn = getattr(handle, name)
+        fn.restype = res
+        fn.argtypes = args
+    return handle
 
 
 def lib() -> ctypes.CDLL:

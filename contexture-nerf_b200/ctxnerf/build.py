@@ -19,6 +19,9 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(PKG_DIR), "csrc")
 BUILD_DIR = os.path.join(CSRC, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libctxnerf.so")
+DIAG_LIB_PATH = os.path.join(PKG_DIR, "libctxnerf_diag.so")   # diagnostics build (include/ctxnerf_diag.h)
+DIAG_DIR = os.path.join(CSRC, "diag")
+DIAG_VARIANT = {"mlp_fwd.cu"}     # product sources that carry #ifdef CTXNERF_DIAG sections
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
@@ -40,11 +43,12 @@ def sources():
 
 def _digest() -> str:
     h = hashlib.sha256()
-    for f in sorted(os.listdir(CSRC)):
-        if f.endswith((".cu", ".cuh", ".h")):
-            h.update(f.encode())
-            with open(os.path.join(CSRC, f), "rb") as fh:
-                h.update(fh.read())
+    for d in (CSRC, DIAG_DIR):
+        for f in sorted(os.listdir(d)):
+            if f.endswith((".cu", ".cuh", ".h")):
+                h.update(f.encode())
+                with open(os.path.join(d, f), "rb") as fh:
+                    h.update(fh.read())
     inc = os.path.join(os.path.dirname(os.path.dirname(PKG_DIR)), "include", "ctxnerf.h")
     if os.path.exists(inc):
         with open(inc, "rb") as fh:
@@ -56,30 +60,40 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(BUILD_DIR, exist_ok=True)
     stamp = os.path.join(BUILD_DIR, "stamp.sha256")
     dig = _digest()
-    if (not force and os.path.exists(LIB_PATH) and os.path.exists(stamp)
+    if (not force and os.path.exists(LIB_PATH) and os.path.exists(DIAG_LIB_PATH) and os.path.exists(stamp)
             and open(stamp).read().strip() == dig):
         return LIB_PATH
     nvcc = _nvcc()
     inc = os.path.join(os.path.dirname(os.path.dirname(PKG_DIR)), "include")
     logs = []
 
-    def compile_one(src):
-        obj = os.path.join(BUILD_DIR, src[:-3] + ".o")
-        cmd = [nvcc, "-c", os.path.join(CSRC, src), "-o", obj, "-I", inc, "-I", CSRC] + ARCH + COMMON
+    def compile_one(job):
+        src_dir, src, diag = job
+        obj = os.path.join(BUILD_DIR, src[:-3] + ("_diag.o" if diag else ".o"))
+        cmd = [nvcc, "-c", os.path.join(src_dir, src), "-o", obj, "-I", inc, "-I", CSRC] + ARCH + COMMON
         if src in NO_FMAD:
             cmd.append("-fmad=false")
+        if diag:
+            cmd.append("-DCTXNERF_DIAG")
         r = subprocess.run(cmd, capture_output=True, text=True)
-        logs.append((src, r.stdout + r.stderr))
+        logs.append((src + (" [diag]" if diag else ""), r.stdout + r.stderr))
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
         return obj
 
+    # product objects, then the extra objects of the diagnostics build: the sources with CTXNERF_DIAG sections
+    # compiled a second time with the macro, and the micro-benchmarks / self-tests of csrc/diag
+    jobs = [(CSRC, s, False) for s in sources()]
+    diag_jobs = [(CSRC, s, True) for s in sorted(DIAG_VARIANT)] + \
+                [(DIAG_DIR, f, True) for f in sorted(os.listdir(DIAG_DIR)) if f.endswith(".cu")]
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
-        objs = list(ex.map(compile_one, sources()))
-    link = [nvcc, "-shared", "-o", LIB_PATH] + objs + ARCH
-    r = subprocess.run(link, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        all_objs = list(ex.map(compile_one, jobs + diag_jobs))
+    objs, diag_objs = all_objs[:len(jobs)], all_objs[len(jobs):]
+    for out, members in ((LIB_PATH, objs),
+                         (DIAG_LIB_PATH, [o for o, j in zip(objs, jobs) if j[1] not in DIAG_VARIANT] + diag_objs)):
+        r = subprocess.run([nvcc, "-shared", "-o", out] + members + ARCH, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     with open(os.path.join(BUILD_DIR, "ptxas.log"), "w") as fh:
         for src, log in sorted(logs):
             fh.write(f"==== {src} ====\n{log}\n")

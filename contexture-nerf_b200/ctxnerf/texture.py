@@ -6,6 +6,8 @@ Drop-in use inside the reference::
 
     from ctxnerf.texture import get_texture_map
     TexturedMeshModel.get_texture_map = lambda self: get_texture_map(self.texture_mlp, self.texture_resolution)
+
+(``self.texture_mlp`` may be the ``nn.DataParallel`` wrapper of trainer.py:134-135: it is unwrapped.)
 """
 from __future__ import annotations
 
@@ -56,7 +58,14 @@ class _TextureMapFn(torch.autograd.Function):
 
 
 def get_texture_map(texture_mlp, res: int):
-    """-> (texture [1,3,res,res] in [0,1], mlp_output [res*res,3]) like the reference method."""
+    """-> (texture [1,3,res,res] in [0,1], mlp_output [res*res,3]) like the reference method.
+
+    ``texture_mlp`` may be the ``nn.DataParallel`` wrapper the reference puts around the MLP on a multi-GPU box
+    (/root/reference/src/training/trainer.py:134-135): the fused query generates its UV grid inside the kernel, there
+    is no input batch to scatter, so it runs on the wrapped module's own device (the wrapper adds nothing here;
+    scattered ``texture_mlp(embedding)`` calls go through DataParallel as usual)."""
+    if isinstance(texture_mlp, torch.nn.DataParallel):
+        texture_mlp = texture_mlp.module
     params = texture_mlp._param_list()
     need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
     return _TextureMapFn.apply(texture_mlp, int(res), need_grad, *params)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CTXNERF_ABI_VERSION 1
+#define CTXNERF_ABI_VERSION 2
 #define CTX_ERR_BAD_ARG (-1)
 #define CTX_ERR_UNSUPPORTED (-2)
 
@@ -215,13 +215,6 @@ int ctx_step_tick(void* counters, float* loss, void* stream);
 int ctx_adam_step_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                       float lr, float beta1, float beta2, float eps, const void* counters, float weight_decay,
                       float grad_scale, void* stream);
-
-/* diagnostic: one-CTA tcgen05 GEMM C[128,N] = A * B^T (tests pin the descriptor
- * conventions with it); A,B bf16.  mode 0 K-major operands, 1 MN-major.          */
-int ctx_tcgen05_selftest(const void* A, const void* B, float* C, int N, int K, int mode, int variant,
-                         void* stream);
-/* same through a 2-CTA cluster: C[256,N] with tcgen05.mma.cta_group::2 (M = 256) */
-int ctx_tcgen05_selftest2(const void* A, const void* B, float* C, int N, int K, void* stream);
 
 #ifdef __cplusplus
 }

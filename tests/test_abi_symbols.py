@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol(libpath):
 def test_python_binding_covers_header(libpath):
     from ctxnerf import _lib
     assert set(declared_symbols()) <= set(_lib._SIGNATURES), set(declared_symbols()) - set(_lib._SIGNATURES)
-    assert _lib.lib().ctx_abi_version() == 1
+    assert _lib.lib().ctx_abi_version() == 2
     assert b"bad argument" in _lib.lib().ctx_error_string(-1)
 
 
@@ -84,3 +84,21 @@ def test_ctypes_signatures_match_the_header_prototypes():
                 assert t is ctypes.c_float, (name, p, t)
             elif p.startswith("int "):
                 assert t is ctypes.c_int, (name, p, t)
+
+
+def test_diagnostics_are_not_part_of_the_product_library(libpath):
+    """tc_selftest micro-benchmarks and the ctx_mlp_set_* profiling hooks live in libctxnerf_diag.so
+    (include/ctxnerf_diag.h); the product library and its header carry none of them."""
+    from ctxnerf import _lib
+    prod = ctypes.CDLL(libpath)
+    diag = ctypes.CDLL(_lib.DIAG_LIB_PATH)
+    text = open(os.path.join(ROOT, "include", "ctxnerf_diag.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    diag_syms = sorted(set(re.findall(r"\b(ctx_[a-z0-9_]+)\s*\(", text)))
+    assert "ctx_tcgen05_selftest" in diag_syms and "ctx_mlp_set_prof_buffer" in diag_syms
+    for sym in diag_syms:
+        assert hasattr(diag, sym), sym
+        assert not hasattr(prod, sym), f"{sym} leaked into the product library"
+        assert sym not in declared_symbols()
+    for sym in declared_symbols():          # the diagnostics build is a superset
+        assert hasattr(diag, sym), sym

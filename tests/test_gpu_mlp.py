@@ -22,9 +22,13 @@ def _diag(msg):
 
 @pytest.mark.parametrize("mode", [0, 1])
 def test_tcgen05_descriptor_conventions(cuda, mode):
-    """One-CTA GEMM through the same descriptor helpers the MLP kernels use."""
+    """One-CTA GEMM through the same descriptor helpers the MLP kernels use (diagnostics build of the library,
+    include/ctxnerf_diag.h: a separate .so, loaded side by side with the product library for this test only)."""
     import ctypes
     from ctxnerf import _lib
+    diag = ctypes.CDLL(_lib.DIAG_LIB_PATH)
+    res_t, arg_t = _lib._DIAG_SIGNATURES["ctx_tcgen05_selftest"]
+    diag.ctx_tcgen05_selftest.restype, diag.ctx_tcgen05_selftest.argtypes = res_t, arg_t
     g = torch.Generator().manual_seed(mode)
     res = {}
     for (N, K) in ((256, 64), (128, 256), (16, 32), (256, 256)):
@@ -35,8 +39,8 @@ def test_tcgen05_descriptor_conventions(cuda, mode):
         Bin = (B if mode == 0 else B.T.contiguous()).to(cuda)
         for variant in (0,):   # variant 1 (swapped LBO/SBO) reads outside shared memory: never run it
             C = torch.zeros(128, N, device=cuda)
-            _lib.call("ctx_tcgen05_selftest", _lib.ptr(Ain), _lib.ptr(Bin), _lib.ptr(C), N, K, mode, variant,
-                      _lib.stream_ptr(cuda))
+            _lib.check(diag.ctx_tcgen05_selftest(_lib.ptr(Ain), _lib.ptr(Bin), _lib.ptr(C), N, K, mode, variant,
+                                                 _lib.stream_ptr(cuda)), "ctx_tcgen05_selftest")
             torch.cuda.synchronize()
             err = (C.cpu() - ref).abs().max().item()
             res[(N, K, variant)] = err

@@ -277,3 +277,45 @@ def test_allreduced_gradients_of_two_ranks_equal_single_process_sum(cuda):
     _diag("dist_check (2 ranks):\n" + r.stdout[-1500:])
     assert r.returncode == 0, r.stderr[-3000:]
     assert r.stdout.count("all-reduced vs single-process sum") == 2
+
+
+def test_drop_in_mlp_survives_nn_dataparallel(cuda):
+    """The reference wraps the texture MLP in nn.DataParallel whenever more than one GPU is visible
+    (/root/reference/src/training/trainer.py:129-135) -- i.e. always on the 8-GPU target.  Build the model exactly as
+    it does, run forward + backward through the wrapper (scatter of the [N,42] embedding, per-device replicas of the
+    parameters, gather, reduce-add of the gradients) and compare with the unwrapped module on one GPU; the fused
+    get_texture_map must accept the wrapper too.  Needs >= 2 GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from ctxnerf import run_nerf_helpers as rh
+    from ctxnerf.texture import get_texture_map
+    device = torch.device("cuda", 0)
+    embed_fn, embedder_out_dim = rh.get_embedder(multires=10)                     # trainer.py:129
+    torch.manual_seed(3)
+    texture_mlp = rh.NeRF2D(D=8, W=256, input_ch=embedder_out_dim, output_ch=3, skips=[4]).to(device)   # :133
+    single = rh.NeRF2D(D=8, W=256, input_ch=embedder_out_dim, output_ch=3, skips=[4]).to(device)
+    single.load_state_dict(texture_mlp.state_dict())
+    wrapped = torch.nn.DataParallel(texture_mlp)                                  # :134-135
+    g = torch.Generator().manual_seed(0)
+    uv = torch.rand(20000, 2, generator=g).to(device)
+    tgt = torch.rand(20000, 3, generator=g).to(device)
+    for step in range(2):       # twice: the replicas are re-broadcast every call (no stale packed weights)
+        out_w = wrapped(embed_fn(uv))
+        out_s = single(embed_fn(uv))
+        assert out_w.shape == out_s.shape == (20000, 3)
+        torch.testing.assert_close(out_w, out_s, rtol=0, atol=1e-6)
+        for m in (texture_mlp, single):
+            m.zero_grad(set_to_none=True)
+        ((torch.tanh(out_w) + 1) / 2 - tgt).pow(2).mean().backward()
+        ((torch.tanh(out_s) + 1) / 2 - tgt).pow(2).mean().backward()
+        for (n, pw), (_, ps) in zip(texture_mlp.named_parameters(), single.named_parameters()):
+            assert pw.grad is not None, n
+            scale = ps.grad.abs().max().item() + 1e-20
+            assert (pw.grad - ps.grad).abs().max().item() <= 2e-5 * scale, (n, step)   # fp32 atomics: order only
+        with torch.no_grad():   # an optimizer step in place, as Adam does (trainer.py:603)
+            for pw, ps in zip(texture_mlp.parameters(), single.parameters()):
+                pw.add_(pw.grad, alpha=-1e-3)
+                ps.add_(ps.grad, alpha=-1e-3)
+    tex_w, _ = get_texture_map(wrapped, 64)
+    tex_s, _ = get_texture_map(single, 64)
+    torch.testing.assert_close(tex_w, tex_s, rtol=0, atol=1e-6)

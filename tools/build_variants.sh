@@ -14,7 +14,7 @@ for spec in "$@"; do
       -O3 -std=c++17 -lineinfo -Xcompiler -fPIC --expt-relaxed-constexpr $flags &
   done
   wait
-  objs=$(ls $PKG/csrc/build/*.o | grep -v "mlp_fwd.o\|mlp_dgrad.o")
+  objs=$(ls $PKG/csrc/build/*.o | grep -v "mlp_fwd.o\|mlp_dgrad.o\|_diag.o")
   nvcc -shared -o $PKG/ctxnerf/variants/libctxnerf_$name.so $objs $tmp/mlp_fwd.o $tmp/mlp_dgrad.o -gencode arch=compute_100a,code=sm_100a
   rm -rf $tmp
   echo built $name

@@ -2,6 +2,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "contexture-nerf_b200")]
 import torch
+from ctxnerf import _lib as _l0; _l0.use_diag_lib()   # diagnostics build (include/ctxnerf_diag.h)
 from ctxnerf import _lib
 dev = torch.device("cuda", 0)
 out = torch.zeros(512, dtype=torch.int64, device=dev)
