@@ -52,6 +52,9 @@ _SIGNATURES = {
     "ctx_tanh01_fwd": (c_int, [P, P, c_int64, c_int, P]),
     "ctx_tanh01_bwd": (c_int, [P, P, P, P, c_int64, c_int, P]),
     "ctx_adam_step": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, c_int, c_float, c_float, P]),
+    "ctx_view_weight_masks": (c_int, [P, P, c_int, c_int, c_int, c_int, P, P, P, P]),
+    "ctx_face_view_map_blocks": (c_int64, [c_int64]),
+    "ctx_face_view_map": (c_int, [P, c_int, c_int, c_int, P, P, c_int, P]),
     "ctx_step_tick": (c_int, [P, P, P]),
     "ctx_adam_step_dev": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, P, c_float, c_float, P]),
     "ctx_mse_fwd_bwd": (c_int, [P, P, P, c_int64, c_float, P, P, P, P]),

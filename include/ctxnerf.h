@@ -216,6 +216,19 @@ int ctx_adam_step_dev(float* params, const float* grads, float* exp_avg, float* 
                       float lr, float beta1, float beta2, float eps, const void* counters, float weight_decay,
                       float grad_scale, void* stream);
 
+/* ---- view-weight masks: ConTEXTure.create_face_view_map / compare_face_normals_between_views,
+ * src/training/trainer.py:155-249 (the reference uses torch_scatter.scatter_max, :227).  face_idx [V,H,W] int64
+ * (< 0 = background), face_normals [V,3,F] fp32.  mask [V,H,W] bytes: 1 unless the pixel's face has a larger
+ * z-normal in another view that shows it.  visible [V*F] bytes / maxz [F] floats: caller-owned scratch.            */
+int ctx_view_weight_masks(const float* face_normals, const int64_t* face_idx, int V, int F, int H, int W,
+                          unsigned char* visible, float* maxz, unsigned char* mask, void* stream);
+/* rows (face, view, i, j) of the covered pixels in (view, pixel) order: pass 0 fills block_counts
+ * [ctx_face_view_map_blocks(V*H*W) + 1] (exclusive offsets; the last entry = number of rows N), pass 1 writes
+ * rows [N,4] int64.                                                                                              */
+int64_t ctx_face_view_map_blocks(int64_t n_pixels);
+int ctx_face_view_map(const int64_t* face_idx, int V, int H, int W, int64_t* block_counts, int64_t* rows, int pass,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

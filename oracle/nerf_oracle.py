@@ -416,6 +416,35 @@ def render_composite(uv, texture, mask, background: float = 1.0, mode: str = "bi
     return img + background * (1 - mask)
 
 
+# --------------------------------------------------------------------------
+# view-weight masks              reference: src/training/trainer.py:155-249
+# --------------------------------------------------------------------------
+
+def create_face_view_map(face_idx: torch.Tensor) -> torch.Tensor:
+    """trainer.py:155-216: rows (face, view, i, j) of every pixel whose face id is >= 0, (view, pixel) order."""
+    V, _, H, W = face_idx.shape
+    flat = face_idx.reshape(V, -1)
+    view, pix = torch.meshgrid(torch.arange(V), torch.arange(H * W), indexing="ij")
+    rows = torch.stack([flat.flatten(), view.flatten(), pix.flatten() // W, pix.flatten() % W], dim=1)
+    return rows[flat.flatten() >= 0]
+
+
+def compare_face_normals_between_views(face_view_map: torch.Tensor, face_normals: torch.Tensor,
+                                       face_idx: torch.Tensor) -> torch.Tensor:
+    """trainer.py:218-249.  torch_scatter.scatter_max(src, index, dim=0) (:227, third party, not in this image) is
+    restated with Tensor.scatter_reduce_('amax', include_self=False): the per-index maximum of the source rows."""
+    V, _, H, W = face_idx.shape
+    masks = torch.full((V, 1, H, W), True, dtype=torch.bool)
+    face_ids, views = face_view_map[:, 0], face_view_map[:, 1]
+    i, j = face_view_map[:, 2], face_view_map[:, 3]
+    z = face_normals[views, 2, face_ids]
+    n_faces = int(face_ids.max().item()) + 1 if face_ids.numel() else 0
+    max_z = torch.full((n_faces,), float("-inf")).scatter_reduce_(0, face_ids, z, "amax", include_self=False)
+    unworthy = z < max_z[face_ids]
+    masks[views, 0, i, j] = ~unworthy
+    return masks
+
+
 def img2mse(x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
     """reference :9"""
     return torch.mean((x - y) ** 2)

@@ -382,3 +382,40 @@ def test_texture_mapping_known_answers(cuda):
         assert torch.allclose(out, torch.flip(tex[0, 0], dims=[0]), atol=1e-5), mode
     e = texture_mapping(torch.empty(1, 0, 2, device=cuda), tex.to(cuda), "bilinear")
     assert e.shape == (1, 0, 1)
+
+
+# ------------------------------------------------------------ view weights ---
+@pytest.mark.parametrize("V,H,W,F", [(7, 300, 300, 5000), (3, 65, 33, 40), (1, 8, 8, 3), (2, 4, 4, 0)])
+def test_view_weight_masks_bit_exact(cuda, V, H, W, F):
+    """create_face_view_map / compare_face_normals_between_views (trainer.py:155-249) against the oracle's restatement
+    (scatter_reduce 'amax' for torch_scatter.scatter_max): int64 rows and boolean masks, exactly."""
+    from ctxnerf import view_weights as vw
+    g = torch.Generator().manual_seed(V * 1000 + F)
+    if F > 0:
+        # piecewise-constant face images (runs of equal ids, as a rasteriser produces) with ~30 % background
+        ids = torch.randint(0, F, (V, 1, H, (W + 3) // 4), generator=g).repeat_interleave(4, dim=3)[..., :W]
+        face_idx = torch.where(torch.rand(V, 1, H, W, generator=g) < 0.3, torch.full_like(ids, -1), ids)
+    else:
+        face_idx = torch.full((V, 1, H, W), -1, dtype=torch.int64)
+    normals = torch.randn(V, 3, max(F, 1), generator=g)[:, :, :F]
+    if F > 3:
+        normals[:, 2, 1] = 0.25                  # ties between views: nobody is "less than the maximum"
+    rows_ref = orc.create_face_view_map(face_idx)
+    mask_ref = orc.compare_face_normals_between_views(rows_ref, normals, face_idx)
+    rows = vw.create_face_view_map(face_idx.to(cuda))
+    assert rows.dtype == torch.int64 and torch.equal(rows.cpu(), rows_ref)
+    mask = vw.compare_face_normals_between_views(rows, normals.to(cuda), face_idx.to(cuda))
+    assert mask.dtype == torch.bool and mask.shape == (V, 1, H, W)
+    assert torch.equal(mask.cpu(), mask_ref)
+    assert torch.equal(vw.view_weight_masks(normals.to(cuda), face_idx.to(cuda)).cpu(), mask_ref)
+
+
+def test_view_weight_masks_against_reference_golden(cuda):
+    """the kernels against the outputs of the reference's own methods (tests/golden/ref_view_weights.npz)."""
+    import os
+    from ctxnerf import view_weights as vw
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_view_weights.npz"))
+    face_idx, normals = torch.from_numpy(g["face_idx"]).to(cuda), torch.from_numpy(g["normals"]).to(cuda)
+    rows = vw.create_face_view_map(face_idx)
+    assert torch.equal(rows.cpu(), torch.from_numpy(g["rows"]))
+    assert torch.equal(vw.compare_face_normals_between_views(rows, normals, face_idx).cpu(), torch.from_numpy(g["masks"]))

@@ -187,3 +187,21 @@ def test_raw2outputs_gradient_agrees_with_hand_derived_fp64():
         ref = raw2outputs_fp64_backward(raw.numpy(), z.numpy(), d.numpy(), g_rgb.numpy(), g_acc.numpy(), g_w.numpy(),
                                         g_depth.numpy(), white_bkgd=white)
         torch.testing.assert_close(r0.grad, torch.from_numpy(ref), rtol=1e-9, atol=1e-12)
+
+
+def test_view_weight_masks_known_answer():
+    """trainer.py:155-249: a face seen by two views keeps only the pixels of the view with the larger z-normal."""
+    face_idx = torch.full((2, 1, 2, 3), -1, dtype=torch.int64)
+    face_idx[0, 0, 0, :2] = 0          # view 0 sees face 0 on two pixels, face 1 on one
+    face_idx[0, 0, 1, 2] = 1
+    face_idx[1, 0, 0, 0] = 0           # view 1 sees face 0 (with a larger z) and face 2
+    face_idx[1, 0, 1, 1] = 2
+    normals = torch.zeros(2, 3, 3)
+    normals[0, 2] = torch.tensor([0.3, 0.5, 0.9])
+    normals[1, 2] = torch.tensor([0.7, 0.9, -0.2])     # face 1 is NOT visible in view 1: its 0.9 must not count
+    rows = orc.create_face_view_map(face_idx)
+    assert rows.tolist() == [[0, 0, 0, 0], [0, 0, 0, 1], [1, 0, 1, 2], [0, 1, 0, 0], [2, 1, 1, 1]]
+    m = orc.compare_face_normals_between_views(rows, normals, face_idx)
+    expect = torch.ones(2, 1, 2, 3, dtype=torch.bool)
+    expect[0, 0, 0, :2] = False        # face 0: view 1 wins (0.7 > 0.3)
+    assert torch.equal(m, expect)
