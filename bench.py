@@ -209,6 +209,71 @@ def run_cfg1(args):
                                        "sample": f"the same chain x{reps}, oracle/nerf_oracle.py"}}), flush=True)
 
 
+def run_inference_cfg(args, which, rank, world, local):
+    """BASELINE configs[1] (--cfg2: 800x800 coarse+fine render, row blocks per rank) and configs[3] (--cfg4: 8 views at
+    1024x1024 x 192 samples, one view per rank) under torchrun: device time of the sharded render (max over ranks) and
+    of the gather to rank 0, plus a bit-equality check of a gathered map against the same render done by rank 0."""
+    import torch.distributed as dist
+    from ctxnerf.dist import render_image_sharded, render_views_sharded
+    from ctxnerf.train import NerfTrainer
+    from ctxnerf.workloads import multiview_cameras, orbit_camera
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    K, c2w = orbit_camera()
+    tr = NerfTrainer(800, 800, K, c2w, near=2.0, far=6.0, perturb=0.0, white_bkgd=True, device=dev, seed=0)
+    cams, sphere = multiview_cameras(8, 1024)
+    if which == "cfg2":
+        work = lambda gather: render_image_sharded(tr, gather=gather)
+        n_rays, evals = 800 * 800, EVALS_PER_RAY
+    else:
+        work = lambda gather: render_views_sharded(tr, cams, 1024, 1024, 192, sphere, gather=gather)
+        n_rays, evals = 8 * 1024 * 1024, 192
+
+    def timed(gather):
+        for _ in range(max(args.warmup, 1)):
+            work(gather)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(args.steps):
+            out = work(gather)
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / args.steps], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item(), out
+    ms_render, _ = timed(False)
+    ms_total, out = timed(True)
+    same = None
+    if rank == 0:
+        if which == "cfg2":
+            ref = tr.render(None)["rgb_map"].reshape(800, 800, 3)
+            same = bool(torch.equal(out["rgb_map"], ref))
+        else:
+            v = min(world, 8) - 1          # a view another rank rendered (the last one of the first round)
+            ref = tr.render_view(1024, 1024, cams[v][0], cams[v][1], n_samples=192, sphere=sphere)["rgb_map"]
+            same = bool(torch.equal(out[v]["rgb_map"], ref))
+        pk = peaks()
+        tf = 2.0 * MACS_PER_EVAL * n_rays * evals / (ms_render * 1e-3) / 1e12
+        print(json.dumps({
+            "metric": "rays/sec inference render", "value": n_rays / (ms_total * 1e-3), "unit": "rays/s", "n_gpus": world,
+            "steps": args.steps, "ms_render": ms_render, "ms_with_gather": ms_total, "scaling": "strong",
+            "config": {"workload": ("configs[1]: 800x800 single view, coarse 64 + fine 128, image row blocks per rank"
+                                    if which == "cfg2" else
+                                    "configs[3]: 8 views 1024x1024 x 192 samples of the napoleon.obj bounding sphere, "
+                                    "one view per rank (round-robin)"), "gather": "maps gathered to rank 0 (NCCL gather)"},
+            "tensor_tflops_all_gpus": tf, "tensor_frac_per_gpu": tf / world / pk["tf_sustained"],
+            "gathered_equals_single_gpu_render": same, "dtype": "bf16", "data": "synthetic"}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -221,6 +286,8 @@ def main():
     ap.add_argument("--cfg1", action="store_true",
                     help="BASELINE configs[0] instead of the training step: raw2outputs(64) -> sample_pdf(det, 128) -> "
                          "merge -> raw2outputs(192) on 4096 rays, GPU chain beside the CPU oracle (parity-test sized)")
+    ap.add_argument("--cfg2", action="store_true", help="BASELINE configs[1]: 800x800 inference render, rows sharded over the ranks")
+    ap.add_argument("--cfg4", action="store_true", help="BASELINE configs[3]: 8 views 1024^2 x 192 samples, views sharded over the ranks")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -231,6 +298,9 @@ def main():
     if args.cfg1:
         if rank == 0:
             run_cfg1(args)
+        return
+    if args.cfg2 or args.cfg4:
+        run_inference_cfg(args, "cfg2" if args.cfg2 else "cfg4", rank, world, local)
         return
 
     import torch.distributed as dist

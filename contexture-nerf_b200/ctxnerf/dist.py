@@ -70,3 +70,85 @@ def world():
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Multi-GPU inference: rays are independent, so inference shards with NO data-path collective --
+# BASELINE config 2 by contiguous row blocks of one image, config 4 by whole views -- and an optional gather of the
+# finished maps to rank 0.  One process per GPU (torchrun); with a single process both functions degenerate to the
+# plain render.
+
+def _gather_rows(t: torch.Tensor, counts, dst: int = 0, group=None):
+    """Gather row blocks of different lengths to ``dst`` (rows padded to the longest block for the collective)."""
+    rank, world_size = world()
+    n_max = max(counts)
+    pad = torch.zeros((n_max,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    pad[:t.shape[0]] = t
+    bufs = [torch.empty_like(pad) for _ in range(world_size)] if rank == dst else None
+    dist.gather(pad, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    return torch.cat([b[:c] for b, c in zip(bufs, counts)], 0)
+
+
+def render_image_sharded(trainer, gather: bool = True, group=None):
+    """BASELINE config 2 on N GPUs: this rank renders the contiguous block of image rows ``shard_rays`` gives it
+    (coarse + fine, deterministic) -- ``trainer.render`` on its pixel range.  Returns the dict of maps of the local
+    rows plus ``"rows": (lo, hi)`` (pixel range); with ``gather`` rank 0 instead gets the full [H, W, ...] maps (other
+    ranks get their local block)."""
+    rank, world_size = world()
+    n = trainer.H * trainer.W
+    lo, hi = shard_rays(n, rank, world_size)
+    idx = torch.arange(lo, hi, device=trainer.device, dtype=torch.int64)
+    out = trainer.render(idx) if hi > lo else None
+    if out is None:       # more ranks than pixels
+        dev = trainer.device
+        out = dict(rgb_map=torch.empty(0, 3, device=dev), disp_map=torch.empty(0, device=dev),
+                   acc_map=torch.empty(0, device=dev), depth_map=torch.empty(0, device=dev),
+                   rgb0=torch.empty(0, 3, device=dev))
+    out["rows"] = (lo, hi)
+    if not gather or world_size == 1:
+        if world_size == 1:
+            out = {k: (v.reshape(trainer.H, trainer.W, *v.shape[1:]) if torch.is_tensor(v) else v) for k, v in out.items()}
+        return out
+    counts = [b - a for a, b in (shard_rays(n, r, world_size) for r in range(world_size))]
+    full = {}
+    for k in ("rgb_map", "disp_map", "acc_map", "depth_map", "rgb0"):
+        g = _gather_rows(out[k], counts, 0, group)
+        if rank == 0:
+            full[k] = g.reshape(trainer.H, trainer.W, *g.shape[1:])
+    if rank == 0:
+        full["rows"] = (0, n)
+        return full
+    return out
+
+
+def render_views_sharded(trainer, cameras, H: int, W: int, n_samples: int = 192, sphere=None, gather: bool = True,
+                         group=None):
+    """BASELINE config 4 on N GPUs: view v is rendered by rank v % N (``trainer.render_view``: single pass of the fine
+    network, per-ray near/far from the bounding sphere).  ``cameras`` = [(K, c2w)].  Returns {view index: maps} for the
+    views of this rank; with ``gather`` rank 0 gets every view's rgb / acc / depth maps (one gather per round of N
+    views, [H,W,5] per rank)."""
+    rank, world_size = world()
+    mine = {}
+    for v, (K, c2w) in enumerate(cameras):
+        if v % world_size == rank:
+            mine[v] = trainer.render_view(H, W, K, c2w, n_samples=n_samples, sphere=sphere)
+    if not gather or world_size == 1:
+        return mine
+    dev = trainer.device
+    out = {}
+    for base in range(0, len(cameras), world_size):
+        v = base + rank
+        if v in mine:
+            m = mine[v]
+            pack = torch.cat([m["rgb_map"], m["acc_map"][..., None], m["depth_map"][..., None]], -1).contiguous()
+        else:
+            pack = torch.zeros(H, W, 5, device=dev)
+        bufs = [torch.empty_like(pack) for _ in range(world_size)] if rank == 0 else None
+        dist.gather(pack, bufs, dst=0, group=group)
+        if rank == 0:
+            for r, b in enumerate(bufs):
+                if base + r < len(cameras):
+                    out[base + r] = dict(rgb_map=b[..., :3], acc_map=b[..., 3], depth_map=b[..., 4])
+    return out if rank == 0 else mine

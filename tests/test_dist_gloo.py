@@ -76,6 +76,76 @@ def test_flat_bucket_allreduce_world2_gloo():
     assert sorted(res) == [(0, "ok"), (1, "ok")], res
 
 
+class _FakeTrainer:
+    """Stands in for NerfTrainer in the host-logic test: 'renders' a deterministic function of the pixel id."""
+    H, W = 5, 7
+    device = torch.device("cpu")
+
+    def render(self, ray_idx):
+        i = (torch.arange(self.H * self.W) if ray_idx is None else ray_idx).float()
+        return dict(rgb_map=torch.stack([i, 2 * i, 3 * i], -1), disp_map=i + 0.5, acc_map=i * 0.25, depth_map=-i,
+                    rgb0=torch.stack([i, i, i], -1))
+
+    def render_view(self, H, W, K, c2w, n_samples=192, sphere=None):
+        base = float(c2w)                       # the fake "pose" is just a number identifying the view
+        img = torch.full((H, W), base) + torch.arange(W).float()
+        return dict(rgb_map=torch.stack([img, img + 1, img + 2], -1), acc_map=img * 0.5, depth_map=img * 2,
+                    disp_map=img)
+
+
+def _render_worker(rank, world, port, q):
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ctxnerf.dist import render_image_sharded, render_views_sharded, shard_rays
+        tr = _FakeTrainer()
+        # config 2: row blocks (35 pixels over 2 ranks: 18 + 17), local result and gathered image
+        local = render_image_sharded(tr, gather=False)
+        lo, hi = shard_rays(35, rank, world)
+        assert local["rows"] == (lo, hi) and local["rgb_map"].shape == (hi - lo, 3)
+        full = render_image_sharded(tr, gather=True)
+        if rank == 0:
+            ref = tr.render(None)
+            for k in ("rgb_map", "disp_map", "acc_map", "depth_map", "rgb0"):
+                assert torch.equal(full[k].reshape(ref[k].shape), ref[k]), k
+            assert full["rgb_map"].shape == (5, 7, 3)
+        # config 4: 5 views round-robin over 2 ranks (rank 0: views 0, 2, 4; rank 1: views 1, 3)
+        cams = [(None, float(10 * v)) for v in range(5)]
+        mine = render_views_sharded(tr, cams, 4, 6, gather=False)
+        assert sorted(mine) == [v for v in range(5) if v % world == rank]
+        allv = render_views_sharded(tr, cams, 4, 6, gather=True)
+        if rank == 0:
+            assert sorted(allv) == [0, 1, 2, 3, 4]
+            for v in range(5):
+                ref = tr.render_view(4, 6, None, float(10 * v))
+                assert torch.equal(allv[v]["rgb_map"], ref["rgb_map"]) and torch.equal(allv[v]["depth_map"], ref["depth_map"])
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_inference_world2_gloo():
+    """render_image_sharded (config 2: row blocks) and render_views_sharded (config 4: views round-robin) with their
+    gathers to rank 0, on two gloo ranks with a fake renderer."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_render_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "ok"), (1, "ok")], res
+
+
 def test_shard_rays_covers_everything():
     from ctxnerf.dist import shard_rays
     for n, w in ((640000, 8), (10, 3), (7, 8), (0, 2)):
