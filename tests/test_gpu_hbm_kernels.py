@@ -419,3 +419,65 @@ def test_view_weight_masks_against_reference_golden(cuda):
     rows = vw.create_face_view_map(face_idx)
     assert torch.equal(rows.cpu(), torch.from_numpy(g["rows"]))
     assert torch.equal(vw.compare_face_normals_between_views(rows, normals, face_idx).cpu(), torch.from_numpy(g["masks"]))
+
+
+# ------------------------------------------- resample: rank-based fast path ---
+@pytest.mark.parametrize("R,S", [(4097, 64), (1001, 128), (300, 192), (100, 256), (33, 512), (5, 4), (2, 3)])
+def test_resample_fast_path_equals_generic_kernel_and_oracle(cuda, R, S):
+    """The rank formulation (monotone u: histogram of first-sample indices + prefix, rank merge) against the generic
+    searchsorted kernel (CTXNERF_RESAMPLE_GENERIC=1) and the oracle: samples, int64 indices and merged depths
+    bit-identical, for every (lanes per ray, items per lane) instantiation."""
+    import os
+    from ctxnerf import ops
+    N = 2 * S
+    g = torch.Generator().manual_seed(S)
+    z = torch.sort(torch.rand(R, S, generator=g) * 4 + 2, -1)[0]
+    w = torch.rand(R, S, generator=g) ** 4
+    w[0] = 0
+    if R > 1:
+        w[1] = 0
+        w[1, S // 2] = 1
+    zc, wc = z.to(cuda), w.to(cuda)
+    zs_f, zall_f, inds_f = ops.resample_merge(zc, wc, N, det=True, return_inds=True)
+    os.environ["CTXNERF_RESAMPLE_GENERIC"] = "1"
+    try:
+        zs_g, zall_g, inds_g = ops.resample_merge(zc, wc, N, det=True, return_inds=True)
+    finally:
+        del os.environ["CTXNERF_RESAMPLE_GENERIC"]
+    assert torch.equal(inds_f, inds_g) and torch.equal(zs_f, zs_g) and torch.equal(zall_f, zall_g)
+    z_mid = 0.5 * (z[..., 1:] + z[..., :-1])
+    s_ref, i_ref = orc.sample_pdf(z_mid, w[..., 1:-1], N, det=True, return_inds=True)
+    assert torch.equal(inds_f.cpu(), i_ref) and torch.equal(zs_f.cpu(), s_ref)
+    assert torch.equal(zall_f.cpu(), torch.sort(torch.cat([z, s_ref], -1), -1)[0])
+    # bare sample_pdf(det=True) takes the same path
+    s2, i2 = ops.resample_raw(z_mid.to(cuda), wc[..., 1:-1].contiguous(), N, det=True)
+    assert torch.equal(s2.cpu(), s_ref) and torch.equal(i2.cpu(), i_ref)
+
+
+def test_resample_merge_with_unsorted_depths_and_sorted_random_uniforms(cuda):
+    """(1) caller-supplied depths that are NOT sorted: the fused call still returns sort(cat[z, samples]) (rank by
+    counting); (2) the in-kernel uniforms of the fused call are drawn already sorted: monotone samples, merged row
+    sorted and equal to the multiset {z} U {samples}, reproducible for a fixed seed, different for another."""
+    from ctxnerf import ops
+    g = torch.Generator().manual_seed(9)
+    R, S, N = 257, 64, 128
+    z = torch.rand(R, S, generator=g) * 4 + 2                 # unsorted
+    w = torch.rand(R, S, generator=g)
+    zs, zall = ops.resample_merge(z.to(cuda), w.to(cuda), N, det=True)
+    z_mid = 0.5 * (z[..., 1:] + z[..., :-1])
+    s_ref = orc.sample_pdf(z_mid, w[..., 1:-1], N, det=True)
+    assert torch.equal(zs.cpu(), s_ref)
+    assert torch.equal(zall.cpu(), torch.sort(torch.cat([z, s_ref], -1), -1)[0])
+    zsrt = torch.sort(z, -1)[0].to(cuda)
+    a_s, a_all = ops.resample_merge(zsrt, w.to(cuda), N, det=False, seed=5)
+    b_s, b_all = ops.resample_merge(zsrt, w.to(cuda), N, det=False, seed=5)
+    c_s, _ = ops.resample_merge(zsrt, w.to(cuda), N, det=False, seed=6)
+    assert torch.equal(a_s, b_s) and torch.equal(a_all, b_all) and not torch.equal(a_s, c_s)
+    assert (a_s[:, 1:] >= a_s[:, :-1]).all() and (a_all[:, 1:] >= a_all[:, :-1]).all()
+    assert torch.equal(a_all, torch.sort(torch.cat([zsrt, a_s], -1), -1)[0])
+    mids = 0.5 * (zsrt[:, 1:] + zsrt[:, :-1])
+    assert (a_s >= mids[:, :1]).all() and (a_s <= mids[:, -1:]).all()
+    # uniform weights -> the samples' empirical cdf over the bin range is close to uniform
+    u_s, _ = ops.resample_merge(zsrt, torch.ones(R, S, device=cuda), N, det=False, seed=7)
+    frac = ((u_s - mids[:, :1]) / (mids[:, -1:] - mids[:, :1])).mean().item()
+    assert 0.45 < frac < 0.55
