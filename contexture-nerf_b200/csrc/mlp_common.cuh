@@ -46,7 +46,9 @@ struct MlpFwdArgs {
   const uint8_t* wpacked;
   const float* fparams;
   // input
-  int mode;                 // 0: pre-encoded x [P, x_ld] fp32, 1: rays + z (encode in-kernel)
+  int mode;                 // 0: pre-encoded x [P, x_ld] fp32, 1: rays + z (encode in-kernel), 2: UV grid generated
+                            // in-kernel, 3: raw points x [*, x_ld = 2|3] (optionally gathered), encoded in-kernel
+  const long long* gather;  // mode 3, nullable: point p reads row gather[p] of x
   const float* x; int x_ld;
   const float* rays_o; const float* rays_d; const float* viewdirs; const float* z;
   int S; int L_pts; int L_dirs;

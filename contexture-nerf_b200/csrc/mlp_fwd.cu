@@ -369,6 +369,18 @@ mlp_fwd_kernel(const __grid_constant__ MlpFwdArgs a) {
           uv[1] = linspace_at(0.0f, 1.0f, res, py);
         }
         encode_row2<CTX_MLP_XP_PAD, 10, 2>(my_x, row, uv, a.L_pts, valid, rec ? rec + net.xp_slot : nullptr);
+      } else if (a.mode == 3) {
+        // raw coordinates, e.g. the rasterised UVs of the texels a mesh actually uses
+        // (reference get_texture_map_only_valid_areas, src/models/textured_mesh.py:303-347), optionally gathered
+        float pt[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+          const int64_t src = a.gather ? a.gather[p] : p;
+          pt[0] = __ldg(a.x + src * a.x_ld);
+          pt[1] = __ldg(a.x + src * a.x_ld + 1);
+          if (a.x_ld > 2) pt[2] = __ldg(a.x + src * a.x_ld + 2);
+        }
+        if (a.x_ld == 2) encode_row2<CTX_MLP_XP_PAD, 10, 2>(my_x, row, pt, a.L_pts, valid, rec ? rec + net.xp_slot : nullptr);
+        else encode_row2<CTX_MLP_XP_PAD, 10, 3>(my_x, row, pt, a.L_pts, valid, rec ? rec + net.xp_slot : nullptr);
       } else {
         float v[CTX_MLP_XP_PAD];
 #pragma unroll
@@ -599,7 +611,7 @@ static void* const ctx_mlp_hang_buffer = nullptr;
 extern "C" int ctx_mlp_fwd_ex(const void* net_host, const void* wpacked, const float* fparams, int mode,
                                const float* x, int x_ld, const float* rays_o, const float* rays_d,
                                const float* viewdirs, const float* z, int S, int L_pts, int L_dirs, int64_t P,
-                               float* out, void* acts, int max_sms, void* stream) {
+                               float* out, void* acts, const int64_t* gather, int max_sms, void* stream) {
   if (P < 0) return CTX_ERR_BAD_ARG;
   if (P == 0) return 0;                       // empty batch: nothing to launch (its pointers may be null)
   if (!net_host || !wpacked || !fparams || !out) return CTX_ERR_BAD_ARG;
@@ -614,9 +626,13 @@ extern "C" int ctx_mlp_fwd_ex(const void* net_host, const void* wpacked, const f
   } else if (mode == 2) {
     if (S < 2 || (int64_t)S * S != P || a.net.in_views != 0) return CTX_ERR_BAD_ARG;
     if (a.net.in_pts != 2 * (1 + 2 * L_pts) || L_pts > 10) return CTX_ERR_UNSUPPORTED;
+  } else if (mode == 3) {
+    if (!x || (x_ld != 2 && x_ld != 3) || a.net.in_views != 0) return CTX_ERR_BAD_ARG;
+    if (a.net.in_pts != x_ld * (1 + 2 * L_pts) || L_pts > 10) return CTX_ERR_UNSUPPORTED;
   } else {
     return CTX_ERR_BAD_ARG;
   }
+  a.gather = (const long long*)gather;
   a.wpacked = (const uint8_t*)wpacked; a.fparams = fparams; a.mode = mode; a.x = x; a.x_ld = x_ld;
   a.rays_o = rays_o; a.rays_d = rays_d; a.viewdirs = viewdirs; a.z = z; a.S = S; a.L_pts = L_pts;
   a.L_dirs = L_dirs; a.P = P; a.out = out; a.acts = (uint8_t*)acts;
@@ -662,5 +678,5 @@ extern "C" int ctx_mlp_fwd(const void* net_host, const void* wpacked, const floa
                             const float* viewdirs, const float* z, int S, int L_pts, int L_dirs, int64_t P,
                             float* out, void* acts, void* stream) {
   return ctx_mlp_fwd_ex(net_host, wpacked, fparams, mode, x, x_ld, rays_o, rays_d, viewdirs, z, S, L_pts, L_dirs, P,
-                        out, acts, 0, stream);
+                        out, acts, nullptr, 0, stream);
 }

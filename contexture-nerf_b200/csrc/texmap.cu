@@ -152,6 +152,76 @@ texmap_rgb4_kernel(const float4* __restrict__ uv, const float* __restrict__ tex,
   }
 }
 
+// ---- bicubic (the third interpolation mode render.py:9 allows): grid_sample's cubic convolution, A = -0.75,
+// align_corners=False, 4 x 4 taps whose INDICES are clipped to the border (padding_mode='border' as kaolin passes).
+struct CubicTaps {
+  int ix[4], iy[4];
+  float cx[4], cy[4];
+};
+__device__ __forceinline__ void cubic_coeffs(float t, float (&c)[4]) {
+  const float A = -0.75f;
+  const float x0 = t + 1.0f, x3 = 2.0f - t, x2 = 1.0f - t;
+  c[0] = ((A * x0 - 5.0f * A) * x0 + 8.0f * A) * x0 - 4.0f * A;
+  c[1] = ((A + 2.0f) * t - (A + 3.0f)) * t * t + 1.0f;
+  c[2] = ((A + 2.0f) * x2 - (A + 3.0f)) * x2 * x2 + 1.0f;
+  c[3] = ((A * x3 - 5.0f * A) * x3 + 8.0f * A) * x3 - 4.0f * A;
+}
+__device__ __forceinline__ CubicTaps cubic_taps(float u, float v, int H, int W) {
+  const float gx = __fsub_rn(__fmul_rn(u, 2.0f), 1.0f);
+  const float gy = -__fsub_rn(__fmul_rn(v, 2.0f), 1.0f);
+  // unnormalise WITHOUT clipping (torch clips the tap indices, not the sampling position, in bicubic mode)
+  const float ix = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.0f), (float)W), 1.0f), 0.5f);
+  const float iy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.0f), (float)H), 1.0f), 0.5f);
+  const float fx = floorf(ix), fy = floorf(iy);
+  CubicTaps t;
+  cubic_coeffs(ix - fx, t.cx);
+  cubic_coeffs(iy - fy, t.cy);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    t.ix[k] = (int)fminf((float)(W - 1), fmaxf(fx - 1.0f + (float)k, 0.0f));
+    t.iy[k] = (int)fminf((float)(H - 1), fmaxf(fy - 1.0f + (float)k, 0.0f));
+  }
+  return t;
+}
+
+template <bool kBwd>
+__global__ void __launch_bounds__(256)
+texmap_bicubic_kernel(const float2* __restrict__ uv, const float* __restrict__ tex, const float* __restrict__ mask,
+                      const float* __restrict__ bg, float* __restrict__ io, float* __restrict__ g_tex, int64_t B,
+                      int64_t N, int tex_batch, int C, int H, int W) {
+  const int64_t total = B * N, plane = (int64_t)H * W;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const float m = mask ? __ldg(mask + i) : 1.0f;
+    if (kBwd && m == 0.f) continue;
+    const int64_t b = i / N;
+    const float2 c = __ldg(uv + i);
+    const CubicTaps t = cubic_taps(c.x, c.y, H, W);
+    const int64_t off = (tex_batch > 1 ? b : 0) * C * plane;
+    for (int ch = 0; ch < C; ++ch) {
+      if (!kBwd) {
+        const float* p = tex + off + ch * plane;
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float row = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) row += t.cx[k] * __ldg(p + (int64_t)t.iy[j] * W + t.ix[k]);
+          acc += t.cy[j] * row;
+        }
+        if (mask) acc = acc * m + (bg ? __ldg(bg + ch) : 0.f) * (1.0f - m);
+        io[i * C + ch] = acc;
+      } else {
+        float* p = g_tex + off + ch * plane;
+        const float g = __ldg(io + i * C + ch) * m;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) atomicAdd(p + (int64_t)t.iy[j] * W + t.ix[k], t.cy[j] * t.cx[k] * g);
+      }
+    }
+  }
+}
+
 static inline bool texmap_vec_ok(int64_t N, int C, std::initializer_list<const void*> ptrs) {
   if (C != 3 || (N & 3) != 0) return false;
   for (const void* p : ptrs)
@@ -168,12 +238,56 @@ static inline int texmap_grid(int64_t total) {
 
 }  // namespace ctx
 
+namespace ctx {
+__global__ void rows_scatter_kernel(const float* __restrict__ src, const long long* __restrict__ idx, float scale,
+                                    float* __restrict__ dst, int64_t M, int C) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < M * C; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = t / C;
+    dst[idx[m] * C + (t - m * C)] = src[t] * scale;
+  }
+}
+__global__ void rows_gather_kernel(const float* __restrict__ g_dst, const long long* __restrict__ idx, float scale,
+                                   float* __restrict__ g_src, int64_t M, int C) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < M * C; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = t / C;
+    g_src[t] = g_dst[idx[m] * C + (t - m * C)] * scale;
+  }
+}
+}  // namespace ctx
+
+extern "C" int ctx_rows_scatter(const float* src, const int64_t* idx, float scale, float* dst, int64_t M, int64_t n,
+                                int C, void* stream) {
+  if (M < 0 || n < 0 || C < 1 || !dst) return CTX_ERR_BAD_ARG;
+  cudaError_t e = cudaMemsetAsync(dst, 0, (size_t)n * C * sizeof(float), (cudaStream_t)stream);
+  if (e != cudaSuccess) return (int)e;
+  if (M == 0) return 0;
+  if (!src || !idx) return CTX_ERR_BAD_ARG;
+  ctx::rows_scatter_kernel<<<ctx::texmap_grid(M * C), 256, 0, (cudaStream_t)stream>>>(src, (const long long*)idx, scale,
+                                                                                     dst, M, C);
+  CTX_RETURN_LAST();
+}
+
+extern "C" int ctx_rows_gather(const float* g_dst, const int64_t* idx, float scale, float* g_src, int64_t M, int C,
+                               void* stream) {
+  if (M < 0 || C < 1) return CTX_ERR_BAD_ARG;
+  if (M == 0) return 0;
+  if (!g_dst || !idx || !g_src) return CTX_ERR_BAD_ARG;
+  ctx::rows_gather_kernel<<<ctx::texmap_grid(M * C), 256, 0, (cudaStream_t)stream>>>(g_dst, (const long long*)idx, scale,
+                                                                                    g_src, M, C);
+  CTX_RETURN_LAST();
+}
+
 extern "C" int ctx_texmap_fwd(const float* uv, const float* tex, const float* mask, const float* bg, float* out,
                               int64_t B, int64_t N, int tex_batch, int C, int H, int W, int mode, void* stream) {
-  if (B < 0 || N < 0 || C < 1 || H < 1 || W < 1 || (mode != 0 && mode != 1)) return CTX_ERR_BAD_ARG;
+  if (B < 0 || N < 0 || C < 1 || H < 1 || W < 1 || mode < 0 || mode > 2) return CTX_ERR_BAD_ARG;
   if (tex_batch != 1 && tex_batch != B) return CTX_ERR_BAD_ARG;
   if (B * N == 0) return 0;
   if (!uv || !tex || !out) return CTX_ERR_BAD_ARG;
+  if (mode == 2) {
+    ctx::texmap_bicubic_kernel<false><<<ctx::texmap_grid(B * N), 256, 0, (cudaStream_t)stream>>>(
+        (const float2*)uv, tex, mask, bg, out, nullptr, B, N, tex_batch, C, H, W);
+    CTX_RETURN_LAST();
+  }
   if (B <= 65535 && ctx::texmap_vec_ok(N, C, {uv, mask, out})) {
     dim3 grid((unsigned)ctx::texmap_grid(N / 4), (unsigned)B);
     ctx::texmap_rgb4_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(
@@ -188,10 +302,15 @@ extern "C" int ctx_texmap_fwd(const float* uv, const float* tex, const float* ma
 // g_tex is ACCUMULATED into (zero it first for a fresh gradient)
 extern "C" int ctx_texmap_bwd(const float* uv, const float* mask, const float* g_out, float* g_tex, int64_t B,
                               int64_t N, int tex_batch, int C, int H, int W, int mode, void* stream) {
-  if (B < 0 || N < 0 || C < 1 || H < 1 || W < 1 || (mode != 0 && mode != 1)) return CTX_ERR_BAD_ARG;
+  if (B < 0 || N < 0 || C < 1 || H < 1 || W < 1 || mode < 0 || mode > 2) return CTX_ERR_BAD_ARG;
   if (tex_batch != 1 && tex_batch != B) return CTX_ERR_BAD_ARG;
   if (B * N == 0) return 0;
   if (!uv || !g_out || !g_tex) return CTX_ERR_BAD_ARG;
+  if (mode == 2) {
+    ctx::texmap_bicubic_kernel<true><<<ctx::texmap_grid(B * N), 256, 0, (cudaStream_t)stream>>>(
+        (const float2*)uv, nullptr, mask, nullptr, const_cast<float*>(g_out), g_tex, B, N, tex_batch, C, H, W);
+    CTX_RETURN_LAST();
+  }
   if (B <= 65535 && ctx::texmap_vec_ok(N, C, {uv, mask, g_out})) {
     dim3 grid((unsigned)ctx::texmap_grid(N / 4), (unsigned)B);
     ctx::texmap_rgb4_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(

@@ -39,7 +39,9 @@ _SIGNATURES = {
     "ctx_mlp_describe": (c_int, [c_int, ctypes.c_uint32, c_int, c_int, c_int, P]),
     "ctx_mlp_pack": (c_int, [P, P, c_int, P, P, P, P]),
     "ctx_mlp_fwd": (c_int, [P, P, P, c_int, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int64, P, P, P]),
-    "ctx_mlp_fwd_ex": (c_int, [P, P, P, c_int, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int64, P, P, c_int, P]),
+    "ctx_mlp_fwd_ex": (c_int, [P, P, P, c_int, P, c_int, P, P, P, P, c_int, c_int, c_int, c_int64, P, P, P, c_int, P]),
+    "ctx_rows_scatter": (c_int, [P, P, c_float, P, c_int64, c_int64, c_int, P]),
+    "ctx_rows_gather": (c_int, [P, P, c_float, P, c_int64, c_int, P]),
     "ctx_mlp_dgrad": (c_int, [P, P, P, P, P, P, c_int64, P]),
     "ctx_mlp_wgrad": (c_int, [P, P, P, c_int64, P, c_int, P, P, P]),
     "ctx_mlp_bwd": (c_int, [P, P, P, P, P, P, c_int64, P, c_int, P, P, P]),

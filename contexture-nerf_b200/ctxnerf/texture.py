@@ -71,6 +71,71 @@ def get_texture_map(texture_mlp, res: int):
     return _TextureMapFn.apply(texture_mlp, int(res), need_grad, *params)
 
 
+class _TextureValidFn(torch.autograd.Function):
+    """MLP at the listed texels only + scatter into the [res*res, C] image (textured_mesh.py:331-347)."""
+
+    @staticmethod
+    def forward(ctx, module, uvs, idx, n_pix, scale, need_grad, *params):
+        module._ensure()
+        desc = module._desc
+        if desc.in_views != 0 or desc.in_pts != 2 * (1 + 2 * module.L_pts):
+            raise _lib.CtxNerfError("the valid-area texture query needs the 2-D texture MLP (no views)")
+        dev = params[0].device
+        M = idx.numel()
+        packed = module._packed.get(list(params))
+        w, wt, f = packed
+        raw = torch.empty(M, desc.out_ch, device=dev, dtype=torch.float32)
+        acts = None
+        if need_grad and M:
+            ntiles = 4 * ((M + 4 * TILE - 1) // (4 * TILE))
+            acts = torch.empty(ntiles * desc.act_tile_bytes, dtype=torch.uint8, device=dev)
+        final = torch.empty(n_pix, desc.out_ch, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            call("ctx_mlp_fwd_ex", desc.p, ptr(w), ptr(f), 3, ptr(uvs), 2, None, None, None, None, 1, module.L_pts, 0, M,
+                 ptr(raw), ptr(acts), ptr(idx), 0, stream_ptr(dev))
+            call("ctx_rows_scatter", ptr(raw), ptr(idx), float(scale), ptr(final), M, n_pix, desc.out_ch, stream_ptr(dev))
+        ctx.module, ctx.M, ctx.acts, ctx.packed, ctx.idx, ctx.scale = module, M, acts, packed, idx, float(scale)
+        return final
+
+    @staticmethod
+    def backward(ctx, g_final):
+        desc = ctx.module._desc
+        if ctx.acts is None:
+            return (None,) * 6 + tuple(None for _ in ctx.needs_input_grad[6:])
+        dev = g_final.device
+        g_raw = torch.empty(ctx.M, desc.out_ch, device=dev, dtype=torch.float32)
+        gf = g_final.float().contiguous()
+        with torch.cuda.device(dev):
+            call("ctx_rows_gather", ptr(gf), ptr(ctx.idx), ctx.scale, ptr(g_raw), ctx.M, desc.out_ch, stream_ptr(dev))
+        grads = mlp_backward(ctx.module, ctx.packed, ctx.acts, ctx.M, g_raw)
+        ctx.acts = None
+        return (None,) * 6 + tuple(grads)
+
+
+def get_texture_map_only_valid_areas(texture_mlp, interpolated_uvs, face_idx, res=None, scale=0.8 / 0.5):
+    """The query + scatter half of the reference's ``get_texture_map_only_valid_areas``
+    (/root/reference/src/models/textured_mesh.py:303-347): the MLP is evaluated ONLY at the texels the UV atlas
+    covers.  ``interpolated_uvs`` [1,res,res,2] and ``face_idx`` [1,res,res] are what the rasteriser returns there
+    (:321-326, kaolin: out of scope); the covered texels are compacted, their UVs gathered and encoded inside the MLP
+    kernel (mode 3), and ``colors * scale`` (``unscale_image``, :336-338) scattered into a zero image.
+    Returns [1, C, res, res].  Gradients flow to the MLP parameters."""
+    from .view_weights import create_face_view_map
+    if isinstance(texture_mlp, torch.nn.DataParallel):
+        texture_mlp = texture_mlp.module
+    if not (interpolated_uvs.is_cuda and face_idx.is_cuda):
+        raise _lib.CtxNerfError("ctxnerf texture queries run on CUDA tensors only (no CPU fallback)")
+    H, W = face_idx.shape[-2], face_idx.shape[-1]
+    if res is not None and (H != res or W != res):
+        raise _lib.CtxNerfError("face_idx does not match the texture resolution")
+    rows = create_face_view_map(face_idx.reshape(1, 1, H, W))          # (face, view, i, j) of the covered texels
+    idx = (rows[:, 2] * W + rows[:, 3]).contiguous()
+    uvs = interpolated_uvs.detach().reshape(H * W, 2).float().contiguous()
+    params = texture_mlp._param_list()
+    need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    final = _TextureValidFn.apply(texture_mlp, uvs, idx, H * W, scale, need_grad, *params)
+    return final.reshape(H, W, -1).permute(2, 0, 1).unsqueeze(0)
+
+
 class _TexMapFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, uv, texture, mask, bg, mode):
@@ -108,16 +173,17 @@ class _TexMapFn(torch.autograd.Function):
         return None, g_tex, None, None, None
 
 
-_MODES = {"nearest": 0, "bilinear": 1}
+_MODES = {"nearest": 0, "bilinear": 1, "bicubic": 2}
 
 
 def texture_mapping(texture_coordinates, texture_maps, mode="nearest", mask=None, background=None):
     """``kal.render.mesh.texture_mapping(uv, texture, mode)`` as used at /root/reference/src/models/render.py:135
     (uv [B,...,2] in [0,1], texture [B or 1, C, H, W] -> [B,...,C]); optionally fused with the two lines that follow
     it there: ``* mask`` and ``+ background * (1 - mask)`` (``mask`` [B,...,1], ``background`` scalar or C values).
-    Only the texture receives a gradient (upstream detaches the coordinates).  'bicubic' is not provided."""
+    Only the texture receives a gradient (upstream detaches the coordinates).  Modes: the three render.py:9 allows
+    ('nearest', 'bilinear', 'bicubic')."""
     if mode not in _MODES:
-        raise _lib.CtxNerfError(f"texture_mapping mode {mode!r} not supported (nearest, bilinear)")
+        raise _lib.CtxNerfError(f"texture_mapping mode {mode!r} not supported (nearest, bilinear, bicubic)")
     bg = None
     if mask is not None and background is not None:
         C = texture_maps.shape[1]

@@ -159,7 +159,7 @@ class NerfTrainer:
         o, d, v, z = rays
         w, _, f = self._pk[net]
         call("ctx_mlp_fwd_ex", net._desc.p, ptr(w), ptr(f), 1, None, 0, ptr(o), ptr(d), ptr(v), ptr(z), z.shape[-1],
-             net.L_pts, net.L_dirs, P, ptr(out), ptr(acts), int(max_sms), stream_ptr(self.device))
+             net.L_pts, net.L_dirs, P, ptr(out), ptr(acts), None, int(max_sms), stream_ptr(self.device))
 
     def _dgrad(self, net, g_raw, acts, dacts, P, max_sms=0):
         _, wt, f = self._pk[net]

@@ -138,11 +138,14 @@ int ctx_mlp_fwd(const void* net, const void* wpacked, const float* fparams, int 
                 const float* z, int S, int L_pts, int L_dirs, int64_t P, float* out, void* acts,
                 void* stream);
 
-/* same with an SM budget (max_sms > 0: at most that many SMs, 0 = the whole GPU), see ctx_mlp_dgrad_ex */
+/* same with an SM budget (max_sms > 0: at most that many SMs, 0 = the whole GPU), see ctx_mlp_dgrad_ex, and with
+ * mode 3: x holds RAW coordinates [*, x_ld] (x_ld = 2 or 3, nets without views), encoded in-kernel with L_pts
+ * frequencies; gather (nullable, int64 [P]): point p reads row gather[p] of x -- the MLP evaluated only at the
+ * texels a mesh uses (get_texture_map_only_valid_areas, src/models/textured_mesh.py:303-347).                  */
 int ctx_mlp_fwd_ex(const void* net, const void* wpacked, const float* fparams, int mode, const float* x,
                    int x_ld, const float* rays_o, const float* rays_d, const float* viewdirs,
                    const float* z, int S, int L_pts, int L_dirs, int64_t P, float* out, void* acts,
-                   int max_sms, void* stream);
+                   const int64_t* gather, int max_sms, void* stream);
 
 /* Backward of ctx_mlp_fwd w.r.t. the parameters (hand-written dgrad + wgrad
  * tcgen05 kernels; the encoded inputs are data and get no gradient).  g_out
@@ -193,6 +196,13 @@ int ctx_texmap_fwd(const float* uv, const float* tex, const float* mask, const f
                    int64_t N, int tex_batch, int C, int H, int W, int mode, void* stream);
 int ctx_texmap_bwd(const float* uv, const float* mask, const float* g_out, float* g_tex, int64_t B, int64_t N,
                    int tex_batch, int C, int H, int W, int mode, void* stream);
+
+/* dst [n,C] = 0 ; dst[idx[m]] = src[m] * scale (m < M)  -- `final_image[mask] = colors` of
+ * get_texture_map_only_valid_areas (:345) -- and its backward g_src[m] = g_dst[idx[m]] * scale.                  */
+int ctx_rows_scatter(const float* src, const int64_t* idx, float scale, float* dst, int64_t M, int64_t n, int C,
+                     void* stream);
+int ctx_rows_gather(const float* g_dst, const int64_t* idx, float scale, float* g_src, int64_t M, int C,
+                    void* stream);
 
 /* ---- training-step glue ------------------------------------------------------
  * img2mse(a,t) + img2mse(b,t) (src/run_nerf_helpers.py:9) and its gradient in one

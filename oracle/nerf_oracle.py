@@ -397,6 +397,21 @@ def texture_map(params, res: int, multires: int = 10, bf16_operands: bool = Fals
     return tex.reshape(1, res, res, 3).permute(0, 3, 1, 2), out
 
 
+def texture_map_only_valid_areas(params, interpolated_uvs: torch.Tensor, face_idx: torch.Tensor, multires: int = 10,
+                                 bf16_operands: bool = False) -> torch.Tensor:
+    """get_texture_map_only_valid_areas from the rasteriser's outputs on (textured_mesh.py:328-347): the MLP at the
+    covered texels only, colours scaled by 0.8/0.5 (unscale_image :336-338), zeros elsewhere -> [1,3,res,res]."""
+    mask = (face_idx >= 0).squeeze(0)
+    uvs = interpolated_uvs.squeeze(0)[mask]
+    res = mask.shape[-1]
+    final = torch.zeros(mask.shape[0], res, 3)
+    if uvs.shape[0] > 0:
+        fwd = mlp_forward_bf16 if bf16_operands else mlp_forward
+        out = fwd(params, posenc(uvs, multires))
+        final[mask] = out / 0.5 * 0.8
+    return final.permute(2, 0, 1).unsqueeze(0)
+
+
 def texture_mapping(uv: torch.Tensor, texture: torch.Tensor, mode: str = "bilinear") -> torch.Tensor:
     """kaolin.render.mesh.texture_mapping as called at /root/reference/src/models/render.py:135 (kaolin is third
     party, un-vendored, no version pinned -> parity unpinned; this restates its documented behaviour): uv [B,...,2] in

@@ -182,6 +182,8 @@ def test_product_fails_loudly_without_cuda():
     with pytest.raises(_lib.CtxNerfError):
         texture_mapping(torch.zeros(1, 4, 2), torch.zeros(1, 3, 8, 8), "bilinear")
     with pytest.raises(_lib.CtxNerfError):
-        texture_mapping(torch.zeros(1, 4, 2), torch.zeros(1, 3, 8, 8), "bicubic")
+        texture_mapping(torch.zeros(1, 4, 2), torch.zeros(1, 3, 8, 8), "bicubic")      # CPU tensors: no fallback
+    with pytest.raises(_lib.CtxNerfError):
+        texture_mapping(torch.zeros(1, 4, 2), torch.zeros(1, 3, 8, 8), "lanczos")
     with pytest.raises((_lib.CtxNerfError, RuntimeError)):
         rh.NeRF2D(D=8, W=256, input_ch=42, output_ch=3, skips=[4])(torch.zeros(4, 42))

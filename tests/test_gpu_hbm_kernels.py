@@ -336,7 +336,7 @@ def test_sample_pdf_backward(cuda):
 
 
 # --------------------------------------------------------- texture mapping ---
-@pytest.mark.parametrize("mode", ["bilinear", "nearest"])
+@pytest.mark.parametrize("mode", ["bilinear", "nearest", "bicubic"])
 @pytest.mark.parametrize("tex_batch", [1, 3])
 @pytest.mark.parametrize("Hh,Ww", [(37, 53), (36, 52)])      # scalar path / four-pixels-per-thread path
 def test_texture_mapping_forward_backward(cuda, mode, tex_batch, Hh, Ww):
@@ -357,8 +357,8 @@ def test_texture_mapping_forward_backward(cuda, mode, tex_batch, Hh, Ww):
     out = texture_mapping(uv.to(cuda), t_gpu, mode, mask=mask.to(cuda), background=1.0)
     (out * gout.to(cuda)).sum().backward()
     assert out.shape == ref.shape
-    if mode == "bilinear":
-        torch.testing.assert_close(out.detach().cpu(), ref.detach(), rtol=1e-5, atol=2e-6)
+    if mode in ("bilinear", "bicubic"):
+        torch.testing.assert_close(out.detach().cpu(), ref.detach(), rtol=1e-5, atol=4e-6)
         torch.testing.assert_close(t_gpu.grad.cpu(), t_ref.grad, rtol=1e-4, atol=1e-5)
     else:   # nearest: a coordinate within an ulp of a texel boundary may pick the neighbour
         same = (out.detach().cpu() - ref.detach()).abs().amax(-1) < 1e-6
@@ -366,8 +366,8 @@ def test_texture_mapping_forward_backward(cuda, mode, tex_batch, Hh, Ww):
     # plain call (no mask), the kaolin signature
     plain = texture_mapping(uv.to(cuda), tex.to(cuda).expand(B, -1, -1, -1).contiguous(), mode)
     ref_plain = orc.texture_mapping(uv, tex.expand(B, -1, -1, -1), mode)
-    if mode == "bilinear":
-        torch.testing.assert_close(plain.cpu(), ref_plain, rtol=1e-5, atol=2e-6)
+    if mode in ("bilinear", "bicubic"):
+        torch.testing.assert_close(plain.cpu(), ref_plain, rtol=1e-5, atol=4e-6)
 
 
 def test_texture_mapping_known_answers(cuda):

@@ -390,3 +390,38 @@ def test_training_converges_on_a_synthetic_target(cuda):
     _diag(f"training sanity: loss {losses[0]:.4f} -> {losses[-1]:.5f}")
     assert all(l == l for l in losses)
     assert losses[-1] < losses[0] / 20
+
+
+def test_texture_map_only_valid_areas(cuda):
+    """get_texture_map_only_valid_areas (textured_mesh.py:303-347), query + scatter half: the MLP runs at the covered
+    texels only (UVs gathered and encoded in-kernel), colours * 0.8/0.5 land in a zero image; forward and parameter
+    gradients against the oracle."""
+    from ctxnerf.texture import get_texture_map_only_valid_areas
+    net, params = _net(cuda, False, seed=77, in_pts=42, out_ch=3)
+    res = 96
+    g = torch.Generator().manual_seed(5)
+    face_idx = torch.where(torch.rand(1, res, res, generator=g) < 0.45, torch.full((1, res, res), -1, dtype=torch.int64),
+                           torch.randint(0, 500, (1, res, res), generator=g))
+    uvs = torch.rand(1, res, res, 2, generator=g)
+    img = get_texture_map_only_valid_areas(net, uvs.to(cuda), face_idx.to(cuda), res)
+    assert img.shape == (1, 3, res, res)
+    pr = {k: t.clone().requires_grad_(True) for k, t in params.items()}
+    ref32 = orc.texture_map_only_valid_areas(params, uvs, face_idx)
+    ref16 = orc.texture_map_only_valid_areas(pr, uvs, face_idx, bf16_operands=True)
+    mask = (face_idx >= 0)[0]
+    assert (img.detach().cpu()[0, :, ~mask] == 0).all()                     # untouched texels stay exactly zero
+    scale = ref32.abs().max().item()
+    e32 = (img.detach().cpu() - ref32).abs().max().item() / scale
+    e16 = (img.detach().cpu() - ref16.detach()).abs().max().item() / scale
+    _diag(f"valid-area texture query: rel err vs fp32 oracle {e32:.3e}, vs bf16 emulation {e16:.3e}")
+    assert e32 < 2e-2 and e16 < 1e-2
+    tgt = torch.rand(1, 3, res, res, generator=g)
+    (img - tgt.to(cuda)).pow(2).mean().backward()
+    (ref16 - tgt).pow(2).mean().backward()
+    for name, p in net.named_parameters():
+        ref = pr[name].grad
+        l2 = ((p.grad.cpu() - ref).norm() / (ref.norm() + 1e-12)).item()
+        assert l2 < 2e-2, (name, l2)
+    # nothing covered: a zero image, no launch failures
+    empty = get_texture_map_only_valid_areas(net, uvs.to(cuda), torch.full((1, res, res), -1, dtype=torch.int64, device=cuda))
+    assert (empty == 0).all()
