@@ -281,6 +281,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the extra 200-step (power-capped) pass")
     ap.add_argument("--ref-rays", type=int, default=0,
                     help="rays per step of the CPU legs (--impl reference / cpu_baseline); default: the full 4096-ray batch")
     ap.add_argument("--cfg1", action="store_true",
@@ -457,6 +458,14 @@ def main():
                 "ms": group_ms, "tensor_tflops": gflops / (group_ms * 1e-3) / 1e12,
                 "tensor_frac": gflops / (group_ms * 1e-3) / 1e12 / pk["tf_sustained"],
                 "hbm_gbs": gbytes / (group_ms * 1e-3) / 1e9, "hbm_frac": gbytes / (group_ms * 1e-3) / 1e9 / pk["hbm_gbs"]}
+    # (last: it heats the board)
+    # ---- the same loop held for 200 steps: the step draws ~1 kW, so after ~50 steps the board's power cap pulls the SM
+    # clock from 1.96 to ~1.6 GHz (profiles/README.md r02); reported beside the 20-step figure, not instead of it ----
+    sustained = None
+    if not args.no_sustained:
+        ms_s, clocks_s, _, _ = timed(lambda i: tr.step(idx_d[i % NB], tgt_d[i % NB]), 200, False)
+        sustained = {"steps": 200, "ms_per_step": ms_s / 200, "value": RAYS_PER_GPU * world * 200 / (ms_s * 1e-3),
+                     "unit": "rays/s", "clocks": clocks_s}
     step_flops = 3 * 2.0 * MACS_PER_EVAL * RAYS_PER_GPU * EVALS_PER_RAY
     line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -469,7 +478,7 @@ def main():
             "step_tensor_frac": step_flops / (ms / args.steps * 1e-3) / 1e12 / pk["tf_sustained"],
             "step_hbm_frac": (REC_BYTES_PER_POINT["fwd"] + REC_BYTES_PER_POINT["dgrad"] + REC_BYTES_PER_POINT["wgrad"])
             * RAYS_PER_GPU * EVALS_PER_RAY / (ms / args.steps * 1e-3) / 1e9 / pk["hbm_gbs"],
-            "kernels": kernels, "final_loss": final_loss}
+            "kernels": kernels, "final_loss": final_loss, "sustained": sustained}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

@@ -1,5 +1,5 @@
 """BASELINE.json configs 2, 4 and 5 on one GPU (config 3 is bench.py, config 1 is the CPU leg).
-Writes gpurun_out/configs_r01.json."""
+Writes gpurun_out/configs_r02.json."""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "contexture-nerf_b200")]
@@ -58,6 +58,15 @@ for lr in (12, 14, 16, 18, 20, 22):
         row = {"rays": R, "samples": S}
         t = timeit(lambda: ops.composite(raw, z, d), iters=3, warm=1)
         row["composite_fwd_gbs"] = R * (24 * S + 36) / t / 1e9
+        # fused training form (forward + loss + backward in one pass): reads raw 16S + z 4S + d 12 + target 12, writes
+        # g_raw 16S + weights 4S
+        tgt = torch.rand(R, 3, device=dev); g_raw = torch.empty_like(raw); wts = torch.empty(R, S, device=dev)
+        loss = torch.zeros(1, device=dev)
+        from ctxnerf._lib import call, ptr, stream_ptr
+        t = timeit(lambda: call("ctx_composite_train", ptr(raw), ptr(z), ptr(d), None, R, S, 1, ptr(tgt), 1.0 / (3 * R),
+                                ptr(loss), ptr(g_raw), ptr(wts), None, stream_ptr(dev)), iters=3, warm=1)
+        row["composite_train_gbs"] = R * (40 * S + 24) / t / 1e9
+        del tgt, g_raw, wts
         N = 2 * S
         if N <= 1024:
             bins_c, w_c = z[:, :S - 1].contiguous(), w[:, :S - 2].contiguous()   # (not part of the timed call)
@@ -76,7 +85,7 @@ for lr in (12, 14, 16, 18, 20, 22):
         torch.cuda.empty_cache()
 out["cfg5_sweep"] = sweep
 os.makedirs("gpurun_out", exist_ok=True)
-json.dump(out, open("gpurun_out/configs_r01.json", "w"), indent=1)
+json.dump(out, open("gpurun_out/configs_r02.json", "w"), indent=1)
 for k, v in out.items():
     if k != "cfg5_sweep":
         print(k, v)
