@@ -191,6 +191,7 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
   const int64_t warp0 = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kCompWarps;
   const int s0 = lane * K;
+  float loss_acc = 0.f;                              // TRAIN: this lane's share of the loss over all its rays
   for (int64_t rb = warp0 * RPW; rb < R; rb += nwarps * RPW) {
     const bool live = rb + sub < R;
     const int64_t ray = live ? rb + sub : R - 1;
@@ -258,10 +259,8 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
       if (lane == 0 && live) {
         if (rgb_out != nullptr) { rgb_out[ray * 3 + 0] = sr + bg; rgb_out[ray * 3 + 1] = sg + bg; rgb_out[ray * 3 + 2] = sb + bg; }
       }
-      // loss: one value per ray (lane 0 of each live group), summed over the warp, one atomic per warp pass
-      float lsum = (lane == 0 && live) ? (er * er + eg * eg + eb * eb) * loss_scale : 0.f;
-      lsum = warp_sum(lsum);
-      if ((threadIdx.x & 31) == 0) atomicAdd(loss, lsum);
+      // loss: one value per ray (lane 0 of each live group), kept in a register over the grid-stride loop
+      if (lane == 0 && live) loss_acc += (er * er + eg * eg + eb * eb) * loss_scale;
     } else {
 #pragma unroll
       for (int k = 0; k < K; ++k) {
@@ -336,6 +335,10 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
         U = Gs[k] * alpha + ((1.0f - alpha) + 1e-10f) * U;
       }
     }
+  }
+  if constexpr (TRAIN) {                             // one atomic per warp for the whole launch
+    loss_acc = warp_sum(loss_acc);
+    if ((threadIdx.x & 31) == 0 && loss_acc != 0.f) atomicAdd(loss, loss_acc);
   }
 }
 

@@ -13,4 +13,9 @@ CTXNERF_GRAPH=0 CTXNERF_OVERLAP=0 ncu --set full --clock-control none --import-s
     -s 12 -c 6 -o gpurun_out/r02/ncu_full_mlp_r02 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-sustained > /dev/null 2>&1
 ncu --set full --clock-control none -k regex:"composite|resample|raygen|posenc|viewmask|faceview" -c 16 \
     -o gpurun_out/r02/ncu_full_hbm_r02 python tools/hbm_once.py > /dev/null 2>&1
+# the .ncu-rep files exceed what gpurun brings back: export the raw pages here and drop them
+for f in ncu_full_mlp_r02 ncu_full_hbm_r02; do
+  ncu -i gpurun_out/r02/$f.ncu-rep --page raw --csv > gpurun_out/r02/${f}_raw.csv 2>/dev/null
+  rm -f gpurun_out/r02/$f.ncu-rep
+done
 ls -la gpurun_out/r02
