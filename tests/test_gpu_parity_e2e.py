@@ -319,3 +319,99 @@ def test_drop_in_mlp_survives_nn_dataparallel(cuda):
     tex_w, _ = get_texture_map(wrapped, 64)
     tex_s, _ = get_texture_map(single, 64)
     torch.testing.assert_close(tex_w, tex_s, rtol=0, atol=1e-6)
+
+
+def test_captured_step_equals_eager_step(cuda):
+    """NerfTrainer.step replays ONE CUDA graph per batch size (device-side seed / Adam step counters, static buffers,
+    SURVEY.md 8f row 3).  Four steps through the graph must leave the same parameters, Adam moments and loss as four
+    eager steps from the same initial state (perturb = 0: no random numbers; fp32 atomics give order-level noise)."""
+    import os
+    from ctxnerf.train import NerfTrainer
+    from ctxnerf.workloads import orbit_camera
+    H = W = 64
+    K, c2w = orbit_camera(H, W, focal=80.0)
+    idx = torch.arange(0, H * W, 3, device=cuda, dtype=torch.int64)[:1024]
+    tgts = [torch.rand(idx.numel(), 3, generator=torch.Generator().manual_seed(s)).to(cuda) for s in range(4)]
+    res = {}
+    for mode in ("graph", "eager"):
+        os.environ["CTXNERF_GRAPH"] = "1" if mode == "graph" else "0"
+        try:
+            tr = NerfTrainer(H, W, K, c2w, perturb=0.0, device=cuda, seed=3, lr=5e-4)
+        finally:
+            del os.environ["CTXNERF_GRAPH"]
+        losses = [tr.step(idx, t).item() for t in tgts]
+        torch.cuda.synchronize()
+        plan = tr._plans[idx.numel()]
+        assert (plan.graph is not None) == (mode == "graph")
+        assert tr._ctr.tolist() == [8, 4]                  # seed offset += 2 and Adam step += 1 per step, on the device
+        res[mode] = (losses, tr.bucket.flat.clone(), tr.exp_avg.clone(), tr.exp_avg_sq.clone())
+    (lg, pg, mg, vg), (le, pe, me, ve) = res["graph"], res["eager"]
+    for a, b in zip(lg, le):
+        assert abs(a - b) <= 1e-4 * abs(b), (lg, le)
+    assert all(l == l for l in lg) and lg[-1] != lg[0]
+    step_size = (pe - NerfTrainer(H, W, K, c2w, perturb=0.0, device=cuda, seed=3).bucket.flat).abs().max().item()
+    assert step_size > 0
+    _diag(f"captured vs eager step: max param diff {(pg - pe).abs().max().item():.3e} (4 Adam steps moved params by "
+          f"{step_size:.3e}), losses {lg[-1]:.6f} / {le[-1]:.6f}")
+    # Adam normalises every update to ~lr: a parameter whose gradient is noise (|g| ~ 1e-9: order-of-summation level)
+    # moves by +-lr whichever sign the noise has, so single parameters may differ by a whole update; the bulk must
+    # agree to a small fraction of it and the first moments to fp32 summation accuracy
+    off = ((pg - pe).abs() > 0.05 * step_size).float().mean().item()
+    _diag(f"captured vs eager step: {100 * off:.3f} % of the parameters differ by more than 5 % of the update size")
+    assert off < 0.01
+    scale_m = me.abs().max().item()
+    assert (mg - me).abs().max().item() <= 2e-3 * scale_m      # (the few flipped updates feed back into later gradients)
+
+
+def test_jitter_changes_between_replays_and_is_reproducible(cuda):
+    """perturb = 1: the stratified jitter and the importance uniforms come from Philox(seed0 + device counter), so two
+    replays of the captured step draw different depths, and two trainers built under the same torch seed agree."""
+    from ctxnerf.train import NerfTrainer
+    from ctxnerf.workloads import orbit_camera
+    H = W = 32
+    K, c2w = orbit_camera(H, W, focal=40.0)
+    idx = torch.arange(H * W, device=cuda)[:512]
+    tgt = torch.rand(512, 3, device=cuda)
+    runs = []
+    for _ in range(2):
+        torch.manual_seed(11)
+        tr = NerfTrainer(H, W, K, c2w, perturb=1.0, device=cuda, seed=1)
+        zs = []
+        for _ in range(3):
+            tr.step(idx, tgt)
+            zs.append(tr._plans[512].z_c.clone())
+        runs.append(zs)
+    assert not torch.equal(runs[0][0], runs[0][1]) and not torch.equal(runs[0][1], runs[0][2])   # fresh numbers per step
+    for a, b in zip(*runs):
+        assert torch.equal(a, b)                                                             # reproducible
+    z = runs[0][2]
+    assert (z[:, 1:] >= z[:, :-1]).all() and z.min() >= 2.0 and z.max() <= 6.0
+
+
+def test_inputs_that_ask_for_unsupported_gradients_raise(cuda):
+    """The hand-written backward differentiates w.r.t. the parameters (MLP) / raw (raw2outputs) only: an input that
+    requires a gradient it would silently not get raises instead; float64 / strided inputs are converted,
+    never reinterpreted."""
+    from ctxnerf import run_nerf_helpers as rh
+    from ctxnerf._lib import CtxNerfError
+    net = rh.NeRF2D(D=8, W=256, input_ch=42, output_ch=3, skips=[4]).to(cuda)
+    x = torch.rand(64, 42, device=cuda, requires_grad=True)
+    with pytest.raises(CtxNerfError):
+        net(x)
+    raw = torch.randn(8, 16, 4, device=cuda, requires_grad=True)
+    z = torch.sort(torch.rand(8, 16, device=cuda) * 4 + 2, -1)[0]
+    d = torch.randn(8, 3, device=cuda)
+    with pytest.raises(CtxNerfError):
+        rh.raw2outputs(raw, z.clone().requires_grad_(True), d)
+    for p in net.parameters():                    # every parameter frozen: forward works, backward is a no-op
+        p.requires_grad_(False)
+    out = net(torch.rand(64, 42, device=cuda))
+    assert not out.requires_grad
+    # float64 ray batch (numpy-built rays, as upstream tolerates): converted
+    nerf = rh.NeRF().to(cuda)
+    rays64 = torch.cat([torch.zeros(16, 3), torch.randn(16, 3), torch.full((16, 1), 2.0), torch.full((16, 1), 6.0),
+                        torch.nn.functional.normalize(torch.randn(16, 3), dim=-1)], -1).double().to(cuda)
+    with torch.no_grad():
+        a = rh.render_rays(rays64, nerf, rh.FusedQuery(), 64, N_importance=32, network_fine=nerf)
+        b = rh.render_rays(rays64.float(), nerf, rh.FusedQuery(), 64, N_importance=32, network_fine=nerf)
+    assert torch.equal(a["rgb_map"], b["rgb_map"])
