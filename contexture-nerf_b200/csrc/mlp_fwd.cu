@@ -35,6 +35,11 @@
 
 namespace ctx {
 
+// Measured and not kept (round 2, profiles/README.md): sixteen epilogue warps on 16-column blocks (four per TMEM lane
+// quarter, 104 registers) -- training forward 0.95 -> 1.01 ms; eight warps on 16-column blocks -- 0.950 -> 0.966 ms:
+// the epilogue is not latency-bound per warp.  A setmaxnreg split must hand out exactly what the CTA was launched with
+// (4 x 56 + 8 x 224 = 12 x 168 here): setmaxnreg.inc only draws on registers the CTA itself released, and a split
+// that asks for more (4 x 56 + 16 x 112 > 20 x 96) hangs the kernel.
 constexpr int kStages2 = 8;          // 8 KB half-chunk stages, handled in PAIRS (one full/empty barrier per pair)
 constexpr int kPairs2 = kStages2 / 2;
 constexpr int kHeadFloats = 648;    // view-direction head block staged in shared memory (w_alpha, W_rgb, biases)

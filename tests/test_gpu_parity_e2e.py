@@ -323,8 +323,11 @@ def test_drop_in_mlp_survives_nn_dataparallel(cuda):
 
 def test_captured_step_equals_eager_step(cuda):
     """NerfTrainer.step replays ONE CUDA graph per batch size (device-side seed / Adam step counters, static buffers,
-    SURVEY.md 8f row 3).  Four steps through the graph must leave the same parameters, Adam moments and loss as four
-    eager steps from the same initial state (perturb = 0: no random numbers; fp32 atomics give order-level noise)."""
+    SURVEY.md 8f row 3).  The first step of a batch size runs eagerly, the second is captured and replayed: after the
+    same first step, the captured second step must produce the gradient bucket, loss and Adam moments of an eager
+    second step (perturb = 0: no random numbers; fp32 atomics give order-level noise).  Parameters are compared in
+    bulk only: Adam normalises every update to ~lr, so a parameter whose gradient is summation noise moves by +-lr
+    whichever sign the noise has."""
     import os
     from ctxnerf.train import NerfTrainer
     from ctxnerf.workloads import orbit_camera
@@ -339,28 +342,29 @@ def test_captured_step_equals_eager_step(cuda):
             tr = NerfTrainer(H, W, K, c2w, perturb=0.0, device=cuda, seed=3, lr=5e-4)
         finally:
             del os.environ["CTXNERF_GRAPH"]
-        losses = [tr.step(idx, t).item() for t in tgts]
+        p0 = tr.bucket.flat.clone()
+        l1 = tr.step(idx, tgts[0]).item()
+        l2 = tr.step(idx, tgts[1]).item()
         torch.cuda.synchronize()
         plan = tr._plans[idx.numel()]
         assert (plan.graph is not None) == (mode == "graph")
+        snap = (l1, l2, tr.bucket.grad.clone(), tr.exp_avg.clone(), tr.bucket.flat.clone())
+        more = [tr.step(idx, t).item() for t in tgts[2:]]          # two more replays
+        torch.cuda.synchronize()
         assert tr._ctr.tolist() == [8, 4]                  # seed offset += 2 and Adam step += 1 per step, on the device
-        res[mode] = (losses, tr.bucket.flat.clone(), tr.exp_avg.clone(), tr.exp_avg_sq.clone())
-    (lg, pg, mg, vg), (le, pe, me, ve) = res["graph"], res["eager"]
-    for a, b in zip(lg, le):
-        assert abs(a - b) <= 1e-4 * abs(b), (lg, le)
-    assert all(l == l for l in lg) and lg[-1] != lg[0]
-    step_size = (pe - NerfTrainer(H, W, K, c2w, perturb=0.0, device=cuda, seed=3).bucket.flat).abs().max().item()
-    assert step_size > 0
-    _diag(f"captured vs eager step: max param diff {(pg - pe).abs().max().item():.3e} (4 Adam steps moved params by "
-          f"{step_size:.3e}), losses {lg[-1]:.6f} / {le[-1]:.6f}")
-    # Adam normalises every update to ~lr: a parameter whose gradient is noise (|g| ~ 1e-9: order-of-summation level)
-    # moves by +-lr whichever sign the noise has, so single parameters may differ by a whole update; the bulk must
-    # agree to a small fraction of it and the first moments to fp32 summation accuracy
-    off = ((pg - pe).abs() > 0.05 * step_size).float().mean().item()
-    _diag(f"captured vs eager step: {100 * off:.3f} % of the parameters differ by more than 5 % of the update size")
-    assert off < 0.01
-    scale_m = me.abs().max().item()
-    assert (mg - me).abs().max().item() <= 2e-3 * scale_m      # (the few flipped updates feed back into later gradients)
+        assert all(l == l for l in more) and torch.isfinite(tr.bucket.flat).all()
+        res[mode] = snap + (p0,)
+    (g1, g2, gg, gm, gp, p0), (e1, e2, eg, em, ep, _) = res["graph"], res["eager"]
+    assert abs(g1 - e1) <= 1e-6 * abs(e1) and abs(g2 - e2) <= 1e-5 * abs(e2), (g1, e1, g2, e2)
+    gscale = eg.abs().max().item()
+    gerr = (gg - eg).abs().max().item() / gscale
+    merr = (gm - em).abs().max().item() / em.abs().max().item()
+    step_size = (ep - p0).abs().max().item()
+    off = ((gp - ep).abs() > 0.05 * step_size).float().mean().item()
+    _diag(f"captured vs eager second step: grad max rel diff {gerr:.3e}, exp_avg {merr:.3e}; {100 * off:.3f} % of the "
+          f"parameters differ by more than 5 % of the update size ({step_size:.3e})")
+    assert gerr < 1e-4 and merr < 1e-4
+    assert off < 0.05
 
 
 def test_jitter_changes_between_replays_and_is_reproducible(cuda):
