@@ -6,10 +6,20 @@
 // HBM-bound: fwd moves 24*S+36 B/ray, bwd 40*S+36 B/ray.
 #include "ctx_common.cuh"
 #include <initializer_list>
+#include <stdlib.h>
 
 namespace ctx {
 
 constexpr int kCompWarps = 8;  // warps per CTA
+// rays longer than this take the chunked kernels (CTXNERF_COMP_SINGLE_MAX overrides it: tests, tuning)
+static inline int comp_single_pass_max() {
+  static const int v = [] {
+    const char* e = getenv("CTXNERF_COMP_SINGLE_MAX");
+    const int x = e ? atoi(e) : 512;
+    return x < 1 ? 1 : (x > 512 ? 512 : x);
+  }();
+  return v;
+}
 
 struct SampleTerms {
   float alpha, trans_factor, expo;  // expo = exp(-relu(sigma)*dist) ; trans_factor = 1-alpha+1e-10
@@ -342,6 +352,245 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Any number of samples per ray: the same blocked scheme run over CHUNKS of 32*K samples with carries -- the
+// transmittance that enters a chunk on the way forward, the value of the reverse recurrence U that enters it on the
+// way back.  Used beyond 512 samples per ray (the single-pass kernels keep a whole ray in registers) and for 257-512,
+// where 16 samples per lane cost more registers than the second pass over a chunk costs time.
+constexpr int kCompMaxChunks = 64;      // per-chunk entry transmittances kept in shared memory by the backward
+
+template <int K>
+__device__ __forceinline__ void chunk_load(const float4* __restrict__ raw, const float* __restrict__ z,
+                                           const float* __restrict__ noise, int64_t base, int c0, int lane, int S,
+                                           float dnorm, float4 (&rw)[K], float (&zl)[K + 1], float (&sig)[K],
+                                           float (&dist)[K]) {
+  const int s0 = c0 + lane * K;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int s = s0 + k;
+    rw[k] = (s < S) ? __ldg(raw + base + s) : make_float4(0.f, 0.f, 0.f, 0.f);
+    zl[k] = (s < S) ? __ldg(z + base + s) : 0.f;
+    sig[k] = rw[k].w + ((noise != nullptr && s < S) ? __ldg(noise + base + s) : 0.f);
+  }
+  zl[K] = (s0 + K < S) ? __ldg(z + base + s0 + K) : 0.f;     // first depth of the next lane / next chunk
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int s = s0 + k;
+    dist[k] = ((s == S - 1) ? 1e10f : (zl[k + 1] - zl[k])) * dnorm;
+  }
+}
+
+template <int K>
+__global__ void __launch_bounds__(kCompWarps * 32)
+composite_chunked_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z,
+                             const float* __restrict__ rays_d, const float* __restrict__ noise, int64_t R, int S,
+                             int white_bkgd, float* __restrict__ rgb_map, float* __restrict__ disp_map,
+                             float* __restrict__ acc_map, float* __restrict__ weights, float* __restrict__ depth_map) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kCompWarps;
+  for (int64_t ray = warp0; ray < R; ray += nwarps) {
+    const float dx = rays_d[ray * 3 + 0], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
+    const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+    const int64_t base = ray * S;
+    float carry = 1.0f, sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f;
+    for (int c0 = 0; c0 < S; c0 += 32 * K) {
+      float4 rw[K];
+      float zl[K + 1], sig[K], dist[K];
+      chunk_load<K>(raw, z, noise, base, c0, lane, S, dnorm, rw, zl, sig, dist);
+      float al[K], pref[K];
+      float run = 1.0f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const bool ok = c0 + lane * K + k < S;
+        const SampleTerms t = sample_terms(sig[k], dist[k]);
+        al[k] = ok ? t.alpha : 0.f;
+        pref[k] = run;
+        run *= ok ? t.trans_factor : 1.0f;
+      }
+      const float incl = group_scan_prod<32>(run, lane);
+      float excl = __shfl_up_sync(CTX_FULL_MASK, incl, 1);
+      if (lane == 0) excl = 1.0f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int s = c0 + lane * K + k;
+        if (s < S) {
+          const float w = al[k] * ((carry * excl) * pref[k]);
+          weights[base + s] = w;
+          sr += w * sigmoidf_(rw[k].x); sg += w * sigmoidf_(rw[k].y); sb += w * sigmoidf_(rw[k].z);
+          sd += w * zl[k]; sa += w;
+        }
+      }
+      carry *= __shfl_sync(CTX_FULL_MASK, incl, 31);
+    }
+    sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sd = warp_sum(sd); sa = warp_sum(sa);
+    if (lane == 0) {
+      const float bg = white_bkgd ? (1.0f - sa) : 0.0f;
+      rgb_map[ray * 3 + 0] = sr + bg; rgb_map[ray * 3 + 1] = sg + bg; rgb_map[ray * 3 + 2] = sb + bg;
+      depth_map[ray] = sd; acc_map[ray] = sa;
+      const float q = sd / sa;
+      disp_map[ray] = (q != q) ? q : 1.0f / fmaxf(1e-10f, q);
+    }
+  }
+}
+
+// backward / fused training form over chunks: pass 1 walks forward (entry transmittance of every chunk, ray totals),
+// pass 2 walks the chunks in reverse with the incoming value of U (see composite_bwd_kernel for the recurrence).
+template <int K, bool TRAIN>
+__global__ void __launch_bounds__(kCompWarps * 32)
+composite_chunked_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z,
+                             const float* __restrict__ rays_d, const float* __restrict__ noise, int64_t R, int S,
+                             int white_bkgd, const float* __restrict__ g_rgb, const float* __restrict__ g_disp,
+                             const float* __restrict__ g_acc, const float* __restrict__ g_weights,
+                             const float* __restrict__ g_depth, float4* __restrict__ g_raw,
+                             const float* __restrict__ target, float loss_scale, float* __restrict__ loss,
+                             float* __restrict__ weights_out, float* __restrict__ rgb_out) {
+  __shared__ float s_carry[kCompWarps][kCompMaxChunks];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp0 = (int64_t)blockIdx.x * kCompWarps + wib;
+  const int64_t nwarps = (int64_t)gridDim.x * kCompWarps;
+  const int n_chunks = (S + 32 * K - 1) / (32 * K);
+  float loss_acc = 0.f;
+  for (int64_t ray = warp0; ray < R; ray += nwarps) {
+    const float dx = rays_d[ray * 3 + 0], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
+    const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+    const int64_t base = ray * S;
+    // ---- pass 1: forward ----
+    float carry = 1.0f, sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f;
+    for (int ci = 0; ci < n_chunks; ++ci) {
+      const int c0 = ci * 32 * K;
+      float4 rw[K];
+      float zl[K + 1], sig[K], dist[K];
+      chunk_load<K>(raw, z, noise, base, c0, lane, S, dnorm, rw, zl, sig, dist);
+      if (lane == 0) s_carry[wib][ci] = carry;
+      float al[K], pref[K];
+      float run = 1.0f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const bool ok = c0 + lane * K + k < S;
+        const SampleTerms t = sample_terms(sig[k], dist[k]);
+        al[k] = ok ? t.alpha : 0.f;
+        pref[k] = run;
+        run *= ok ? t.trans_factor : 1.0f;
+      }
+      const float incl = group_scan_prod<32>(run, lane);
+      float excl = __shfl_up_sync(CTX_FULL_MASK, incl, 1);
+      if (lane == 0) excl = 1.0f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const int s = c0 + lane * K + k;
+        if (s < S) {
+          const float w = al[k] * ((carry * excl) * pref[k]);
+          if (TRAIN && weights_out != nullptr) weights_out[base + s] = w;
+          if (TRAIN) { sr += w * sigmoidf_(rw[k].x); sg += w * sigmoidf_(rw[k].y); sb += w * sigmoidf_(rw[k].z); }
+          sd += w * zl[k]; sa += w;
+        }
+      }
+      carry *= __shfl_sync(CTX_FULL_MASK, incl, 31);
+    }
+    sd = warp_sum(sd); sa = warp_sum(sa);
+    float gr, gg, gb, gd, ga;
+    if constexpr (TRAIN) {
+      sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb);
+      const float bg = white_bkgd ? (1.0f - sa) : 0.0f;
+      const float er = sr + bg - target[ray * 3 + 0], eg = sg + bg - target[ray * 3 + 1], eb = sb + bg - target[ray * 3 + 2];
+      gr = 2.0f * er * loss_scale; gg = 2.0f * eg * loss_scale; gb = 2.0f * eb * loss_scale;
+      gd = 0.f; ga = 0.f;
+      if (lane == 0) {
+        if (rgb_out != nullptr) { rgb_out[ray * 3 + 0] = sr + bg; rgb_out[ray * 3 + 1] = sg + bg; rgb_out[ray * 3 + 2] = sb + bg; }
+        loss_acc += (er * er + eg * eg + eb * eb) * loss_scale;
+      }
+    } else {
+      gr = g_rgb ? g_rgb[ray * 3 + 0] : 0.f; gg = g_rgb ? g_rgb[ray * 3 + 1] : 0.f; gb = g_rgb ? g_rgb[ray * 3 + 2] : 0.f;
+      gd = g_depth ? g_depth[ray] : 0.f;
+      ga = g_acc ? g_acc[ray] : 0.f;
+      const float gdisp = g_disp ? g_disp[ray] : 0.f;
+      if (gdisp != 0.f) {
+        const float q = sd / sa;
+        if (q > 1e-10f) {
+          const float dq = -gdisp / (q * q);
+          gd += dq / sa;
+          ga += -dq * sd / (sa * sa);
+        } else if (q != q) {
+          gd = q; ga = q;
+        }
+      }
+    }
+    if (white_bkgd) ga -= (gr + gg + gb);
+    __syncwarp();
+    // ---- pass 2: reverse ----
+    float carryU = 0.f;                         // U just past the end of the chunk being processed
+    for (int ci = n_chunks - 1; ci >= 0; --ci) {
+      const int c0 = ci * 32 * K;
+      float4 rw[K];
+      float zl[K + 1], sig[K], dist[K];
+      chunk_load<K>(raw, z, noise, base, c0, lane, S, dnorm, rw, zl, sig, dist);
+      const float cin = s_carry[wib][ci];
+      float ex[K], pref[K], Gs[K];
+      float run = 1.0f;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const bool ok = c0 + lane * K + k < S;
+        const SampleTerms t = sample_terms(sig[k], dist[k]);
+        ex[k] = ok ? t.expo : 1.0f;
+        pref[k] = run;
+        run *= ok ? t.trans_factor : 1.0f;
+      }
+      const float incl = group_scan_prod<32>(run, lane);
+      float excl = __shfl_up_sync(CTX_FULL_MASK, incl, 1);
+      if (lane == 0) excl = 1.0f;
+      // the lane's composed map  U_first = Bc + A * U_(first sample of the next lane)
+      float A = 1.0f, Bc = 0.f;
+#pragma unroll
+      for (int k = K - 1; k >= 0; --k) {
+        const int s = c0 + lane * K + k;
+        const bool ok = s < S;
+        const float cr = sigmoidf_(rw[k].x), cg = sigmoidf_(rw[k].y), cb = sigmoidf_(rw[k].z);
+        const float gw = (!TRAIN && g_weights != nullptr && ok) ? __ldg(g_weights + base + s) : 0.f;
+        Gs[k] = gw + gr * cr + gg * cg + gb * cb + gd * zl[k] + ga;
+        const float alpha = 1.0f - ex[k];
+        const float a = ok ? ((1.0f - alpha) + 1e-10f) : 1.0f;
+        const float b = ok ? Gs[k] * alpha : 0.f;
+        Bc = b + a * Bc;
+        A = a * A;
+      }
+      float a = A, b = Bc;                      // inclusive suffix composition over the lanes [lane, 32)
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float a2 = __shfl_down_sync(CTX_FULL_MASK, a, o);
+        const float b2 = __shfl_down_sync(CTX_FULL_MASK, b, o);
+        if (lane + o < 32) { b = b + a * b2; a = a * a2; }
+      }
+      // U at the first sample of the NEXT lane = map of lanes (lane, 32) applied to carryU
+      float an = __shfl_down_sync(CTX_FULL_MASK, a, 1), bn = __shfl_down_sync(CTX_FULL_MASK, b, 1);
+      if (lane == 31) { an = 1.0f; bn = 0.f; }
+      float U = bn + an * carryU;
+#pragma unroll
+      for (int k = K - 1; k >= 0; --k) {
+        const int s = c0 + lane * K + k;
+        if (s < S) {
+          const float alpha = 1.0f - ex[k];
+          const float T = (cin * excl) * pref[k];
+          const float cr = sigmoidf_(rw[k].x), cg = sigmoidf_(rw[k].y), cb = sigmoidf_(rw[k].z);
+          const float g_alpha = T * (Gs[k] - U);
+          const float g_sigma = (sig[k] > 0.f) ? g_alpha * ex[k] * dist[k] : 0.f;
+          const float w = alpha * T;
+          g_raw[base + s] = make_float4(w * gr * cr * (1.0f - cr), w * gg * cg * (1.0f - cg), w * gb * cb * (1.0f - cb), g_sigma);
+          U = Gs[k] * alpha + ((1.0f - alpha) + 1e-10f) * U;
+        }
+      }
+      // U at the first sample of this chunk = whole-chunk map applied to the incoming value
+      const float a0 = __shfl_sync(CTX_FULL_MASK, a, 0), b0 = __shfl_sync(CTX_FULL_MASK, b, 0);
+      carryU = b0 + a0 * carryU;
+    }
+    __syncwarp();
+  }
+  if constexpr (TRAIN) {
+    loss_acc = warp_sum(loss_acc);
+    if (lane == 0 && loss_acc != 0.f) atomicAdd(loss, loss_acc);
+  }
+}
+
 // widest vector access (floats) that is aligned for every [R,S] row of the given pointers
 static inline int comp_vec(int S, std::initializer_list<const void*> ptrs) {
   int vec = (S % 4 == 0) ? 4 : (S % 2 == 0 ? 2 : 1);
@@ -389,13 +638,20 @@ extern "C" int ctx_composite_fwd(const float* raw, const float* z_vals, const fl
                                  const float* noise, int64_t R, int S, int white_bkgd,
                                  float* rgb_map, float* disp_map, float* acc_map, float* weights,
                                  float* depth_map, void* stream) {
-  if (R < 0 || S < 1 || S > 512) return CTX_ERR_BAD_ARG;
+  if (R < 0 || S < 1 || S > 256 * ctx::kCompMaxChunks) return CTX_ERR_BAD_ARG;
   if (R == 0) return 0;
   if (!raw || !z_vals || !rays_d || !rgb_map || !disp_map || !acc_map || !weights || !depth_map)
     return CTX_ERR_BAD_ARG;
   if (reinterpret_cast<uintptr_t>(raw) % 16 != 0) return CTX_ERR_BAD_ARG;   // raw is read as float4 (128-bit loads)
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ctx::comp_grid(R, S), block = ctx::kCompWarps * 32;
+  // (forward: beyond 384 samples the 16-samples-per-lane single pass is slower than two chunks of 8 per lane --
+  //  36 % vs 52 % of the copy bandwidth at S = 512; the backward keeps its single pass up to 512: 41 % vs 36 %)
+  if (S > (ctx::comp_single_pass_max() < 384 ? ctx::comp_single_pass_max() : 384)) {
+    ctx::composite_chunked_fwd_kernel<8><<<grid, block, 0, st>>>((const float4*)raw, z_vals, rays_d, noise, R, S,
+                                                                white_bkgd, rgb_map, disp_map, acc_map, weights, depth_map);
+    CTX_RETURN_LAST();
+  }
   const int vec = ctx::comp_vec(S, {z_vals, noise, weights});
   CTX_COMP_DISPATCH(ctx::composite_fwd_kernel, (const float4*)raw, z_vals, rays_d, noise, R, S, vec,
                     white_bkgd, rgb_map, disp_map, acc_map, weights, depth_map)
@@ -407,13 +663,19 @@ extern "C" int ctx_composite_bwd(const float* raw, const float* z_vals, const fl
                                  const float* g_rgb, const float* g_disp, const float* g_acc,
                                  const float* g_weights, const float* g_depth, float* g_raw,
                                  void* stream) {
-  if (R < 0 || S < 1 || S > 512) return CTX_ERR_BAD_ARG;
+  if (R < 0 || S < 1 || S > 256 * ctx::kCompMaxChunks) return CTX_ERR_BAD_ARG;
   if (R == 0) return 0;
   if (!raw || !z_vals || !rays_d || !g_raw) return CTX_ERR_BAD_ARG;
   if (reinterpret_cast<uintptr_t>(raw) % 16 != 0 || reinterpret_cast<uintptr_t>(g_raw) % 16 != 0)
     return CTX_ERR_BAD_ARG;                                                  // float4 loads / stores
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ctx::comp_grid(R, S), block = ctx::kCompWarps * 32;
+  if (S > ctx::comp_single_pass_max()) {
+    ctx::composite_chunked_bwd_kernel<8, false><<<grid, block, 0, st>>>(
+        (const float4*)raw, z_vals, rays_d, noise, R, S, white_bkgd, g_rgb, g_disp, g_acc, g_weights, g_depth,
+        (float4*)g_raw, nullptr, 0.f, nullptr, nullptr, nullptr);
+    CTX_RETURN_LAST();
+  }
   const int vec = ctx::comp_vec(S, {z_vals, noise, g_weights});
   CTX_COMP_DISPATCH_BWD(false, (const float4*)raw, z_vals, rays_d, noise, R, S, vec, white_bkgd, g_rgb, g_disp,
                         g_acc, g_weights, g_depth, (float4*)g_raw, nullptr, 0.f, nullptr, nullptr, nullptr)
@@ -426,13 +688,19 @@ extern "C" int ctx_composite_bwd(const float* raw, const float* z_vals, const fl
 extern "C" int ctx_composite_train(const float* raw, const float* z_vals, const float* rays_d, const float* noise,
                                    int64_t R, int S, int white_bkgd, const float* target, float loss_scale,
                                    float* loss, float* g_raw, float* weights, float* rgb_map, void* stream) {
-  if (R < 0 || S < 1 || S > 512) return CTX_ERR_BAD_ARG;
+  if (R < 0 || S < 1 || S > 256 * ctx::kCompMaxChunks) return CTX_ERR_BAD_ARG;
   if (R == 0) return 0;
   if (!raw || !z_vals || !rays_d || !target || !loss || !g_raw) return CTX_ERR_BAD_ARG;
   if (reinterpret_cast<uintptr_t>(raw) % 16 != 0 || reinterpret_cast<uintptr_t>(g_raw) % 16 != 0)
     return CTX_ERR_BAD_ARG;
   cudaStream_t st = (cudaStream_t)stream;
   const int grid = ctx::comp_grid(R, S), block = ctx::kCompWarps * 32;
+  if (S > ctx::comp_single_pass_max()) {
+    ctx::composite_chunked_bwd_kernel<8, true><<<grid, block, 0, st>>>(
+        (const float4*)raw, z_vals, rays_d, noise, R, S, white_bkgd, nullptr, nullptr, nullptr, nullptr, nullptr,
+        (float4*)g_raw, target, loss_scale, loss, weights, rgb_map);
+    CTX_RETURN_LAST();
+  }
   const int vec = ctx::comp_vec(S, {z_vals, noise, weights});
   CTX_COMP_DISPATCH_BWD(true, (const float4*)raw, z_vals, rays_d, noise, R, S, vec, white_bkgd, nullptr, nullptr,
                         nullptr, nullptr, nullptr, (float4*)g_raw, target, loss_scale, loss, weights, rgb_map)

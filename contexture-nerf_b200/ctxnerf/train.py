@@ -120,6 +120,10 @@ class NerfTrainer:
         # does not depend on the fine pass), beside resample + fwd_fine + dgrad_fine, which then take main_sms SMs
         self.early_coarse = os.environ.get("CTXNERF_EARLY_COARSE", "0") == "1"
         self.main_sms = _env_int("CTXNERF_MAIN_SMS", n_sm - self.side_sms)
+        # CTXNERF_SCHED=queue: both backward chains at full grid size on two streams, no SM budgets: the hardware hands
+        # an SM to the next kernel's CTA as soon as one of the running kernel's CTAs retires (no drain / fill bubble
+        # between launches); measured against the budgeted schedule in profiles/README.md
+        self.sched_queue = os.environ.get("CTXNERF_SCHED", "") == "queue"
         self.use_graph = os.environ.get("CTXNERF_GRAPH", "1") != "0"
         self._side = torch.cuda.Stream(device=dev)
         self._pack_stream = torch.cuda.Stream(device=dev)
@@ -213,6 +217,16 @@ class NerfTrainer:
         msm = self.main_sms if early else 0
         self._timed("mlp_fwd_fine", lambda: self._fwd(self.fine, rays_f, Pf, pl.raw_f, pl.acts_f, max_sms=msm))
         self._comp_train(pl.raw_f, pl.z_f, pl.d, R, Sf, pl.target, pl.g_raw_f, None, pl.rgb)
+        if self.sched_queue and self.overlap_backward and not early:
+            self._ev0.record(main)
+            self._side.wait_event(self._ev0)
+            self._dgrad(self.fine, pl.g_raw_f, pl.acts_f, pl.dacts_f, Pf)
+            with torch.cuda.stream(self._side):
+                coarse_chain(0, 0)
+                self._ev1.record(self._side)
+            self._wgrad(self.fine, pl.acts_f, pl.dacts_f, Pf)
+            main.wait_event(self._ev1)
+            return
         self._timed("mlp_dgrad_fine",
                     lambda: self._dgrad(self.fine, pl.g_raw_f, pl.acts_f, pl.dacts_f, Pf, max_sms=msm))
         if early:

@@ -72,7 +72,8 @@ int ctx_ndc_bwd(int H, int W, float focal, float near, const float* rays_o, cons
  * src/run_nerf_helpers.py:131-133; spec SURVEY.md 8c-S1) -----------------------
  * raw [R,S,4], z_vals [R,S], rays_d [R,3], noise (nullable, [R,S], already
  * scaled by raw_noise_std) -> rgb [R,3], disp [R], acc [R], weights [R,S],
- * depth [R].  S <= 512.                                                        */
+ * depth [R].  Any S up to 16384 (rays longer than 512 samples run a chunked variant
+ * of the same scan).                                                             */
 int ctx_composite_fwd(const float* raw, const float* z_vals, const float* rays_d,
                       const float* noise, int64_t R, int S, int white_bkgd, float* rgb_map,
                       float* disp_map, float* acc_map, float* weights, float* depth_map,
@@ -105,7 +106,7 @@ int ctx_resample_bwd(const float* bins, int64_t bins_stride, int mid_bins, const
  * (src/run_nerf_helpers.py:9) + backward in ONE pass over raw.  g_raw [R,S,4] = d loss / d raw with
  * loss = sum((rgb_map - target)^2) * loss_scale (loss_scale = 1/(3R) for the image mean); loss[0] += that value
  * (zero it once per step; the coarse and the fine pass add into the same scalar).  weights [R,S] and rgb_map [R,3]
- * are optional outputs (the coarse pass feeds sample_pdf with its weights).  S <= 512.                        */
+ * are optional outputs (the coarse pass feeds sample_pdf with its weights).                        */
 int ctx_composite_train(const float* raw, const float* z_vals, const float* rays_d, const float* noise,
                         int64_t R, int S, int white_bkgd, const float* target, float loss_scale, float* loss,
                         float* g_raw, float* weights, float* rgb_map, void* stream);

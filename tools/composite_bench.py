@@ -10,8 +10,8 @@ def timeit(fn, n=10):
     for _ in range(4): fn()
     torch.cuda.synchronize(); a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); [fn() for _ in range(n)]; b.record(); torch.cuda.synchronize(); return a.elapsed_time(b) / n * 1e-3
-R = 1 << 20
-for S in (32, 64, 128, 192, 256):
+R = 1 << (19 if "--small" in sys.argv else 20)
+for S in (32, 64, 128, 192, 256, 384, 512):
     raw = torch.randn(R, S, 4, device=dev); raw[..., 3] *= 5
     z = torch.sort(torch.rand(R, S, device=dev) * 4 + 2, -1)[0]; d = torch.randn(R, 3, device=dev)
     rr = raw.clone().requires_grad_(True); outs = ops.composite(rr, z, d)
