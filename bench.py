@@ -34,7 +34,8 @@ CONFIG = {"workload": "configs[2]: training step fwd+bwd, 4096-ray batch per GPU
           "rays_per_gpu": RAYS_PER_GPU, "n_samples": N_SAMPLES, "n_importance": N_IMPORTANCE,
           "image": "800x800 config-2 camera", "perturb": 1.0, "white_bkgd": True,
           "l2": "no explicit flush: each step streams ~15 GB of activation / dZ records through the 126 MB L2",
-          "schedule": "one CUDA graph per step (two around the all-reduce when N > 1); backward of the coarse network "
+          "schedule": "one CUDA graph per step (N > 1: the NCCL all-reduce of the gradient bucket is a node of it, issued "
+                      "through the library's ctx_allreduce); backward of the coarse network "
                       "(dgrad -> wgrad) on a side stream beside wgrad of the fine network (SM budgets 44 / 104)"}
 
 
@@ -479,6 +480,11 @@ def main():
             "step_hbm_frac": (REC_BYTES_PER_POINT["fwd"] + REC_BYTES_PER_POINT["dgrad"] + REC_BYTES_PER_POINT["wgrad"])
             * RAYS_PER_GPU * EVALS_PER_RAY / (ms / args.steps * 1e-3) / 1e9 / pk["hbm_gbs"],
             "kernels": kernels, "final_loss": final_loss, "sustained": sustained}
+    if world > 1:
+        line["allreduce"] = {"route": "ctx_allreduce (libctxnerf NCCL binding, inside the step graph)" if tr.comm is not None
+                             else "torch.distributed between two graphs",
+                             "nccl_version": tr.comm.version if tr.comm is not None else None,
+                             "bytes": 4 * tr.bucket.numel}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1

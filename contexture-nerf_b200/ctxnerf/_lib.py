@@ -60,6 +60,13 @@ _SIGNATURES = {
     "ctx_step_tick": (c_int, [P, P, P]),
     "ctx_adam_step_dev": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, P, c_float, c_float, P]),
     "ctx_mse_fwd_bwd": (c_int, [P, P, P, c_int64, c_float, P, P, P, P]),
+    "ctx_comm_load": (c_int, [ctypes.c_char_p]),
+    "ctx_comm_version": (c_int, []),
+    "ctx_comm_last_error": (ctypes.c_char_p, []),
+    "ctx_comm_unique_id": (c_int, [P]),
+    "ctx_comm_init": (c_int, [P, c_int, P, c_int]),
+    "ctx_comm_destroy": (c_int, [P]),
+    "ctx_allreduce": (c_int, [P, P, c_int64, P]),
 }
 
 
@@ -121,11 +128,15 @@ def lib() -> ctypes.CDLL:
 def check(code: int, what: str) -> None:
     if code != 0:
         msg = lib().ctx_error_string(int(code))
-        raise CtxNerfError(f"{what} failed with code {code}: {msg.decode() if msg else '?'}")
+        text = msg.decode() if msg else "?"
+        if code == -3:      # CTX_ERR_NO_NCCL: the detail lives in the communicator binding
+            detail = lib().ctx_comm_last_error()
+            text += f" [{detail.decode() if detail else ''}]"
+        raise CtxNerfError(f"{what} failed with code {code}: {text}")
 
 
 # kernels launched per ABI call (bench.py reports the total as gpu_launches)
-KERNELS_PER_CALL = {"ctx_mlp_bwd": 2}     # (the view-direction wgrad also runs a small post kernel: +1, counted by the callers that know the net)
+KERNELS_PER_CALL = {"ctx_mlp_bwd": 2, "ctx_allreduce": 0, "ctx_comm_load": 0, "ctx_comm_unique_id": 0, "ctx_comm_init": 0, "ctx_comm_destroy": 0}     # (the view-direction wgrad also runs a small post kernel: +1, counted by the callers that know the net)
 launch_count = 0
 
 

@@ -4,12 +4,18 @@ resident, ONE all-reduce of a flat fp32 gradient bucket per step.
 Replaces the reference's only parallel construct, nn.DataParallel around the
 MLP (/root/reference/src/training/trainer.py:134-135: per-forward weight
 broadcast + input scatter + output gather + reduce-add onto GPU 0).  The path
-shards by rays with no data-path collective; the gradient all-reduce goes
-through torch.distributed (NCCL over NVLink on the GPU box, gloo in CPU tests).
+shards by rays with no data-path collective.  The gradient all-reduce is NCCL
+over NVLink: on the GPU through the library's own binding (``BucketComm`` ->
+ctx_allreduce of include/ctxnerf.h, enqueued on the step's stream so that the
+whole step -- all-reduce included -- is ONE captured CUDA graph), else through
+torch.distributed (gloo in the CPU tests, or CTXNERF_NCCL=0).
 """
 from __future__ import annotations
 
 from typing import List, Sequence
+
+import ctypes
+import os
 
 import torch
 import torch.distributed as dist
@@ -51,6 +57,57 @@ class FlatBucket:
         return None
 
 
+def _loaded_nccl_path():
+    """Path of the NCCL shared object already mapped into this process (torch's bundled copy), so that the C-ABI
+    binding and torch.distributed use the same library; None -> the binding falls back to the soname."""
+    try:
+        with open("/proc/self/maps") as fh:
+            for line in fh:
+                if "libnccl.so" in line:
+                    return line.split()[-1]
+    except OSError:
+        pass
+    return None
+
+
+class BucketComm:
+    """NCCL communicator of the C-ABI (ctx_comm_* / ctx_allreduce, include/ctxnerf.h) over the ranks of the
+    initialised torch.distributed group: rank 0 makes the rendezvous token, torch.distributed carries its 128 bytes
+    to the other ranks, every rank then joins on its own device.  ``all_reduce`` enqueues on the CURRENT stream."""
+
+    def __init__(self, device, group=None):
+        from . import _lib
+        self._lib = _lib
+        rank, world_size = world()
+        if world_size < 2:
+            raise RuntimeError("BucketComm needs an initialised torch.distributed group with more than one rank")
+        path = os.environ.get("CTXNERF_NCCL_LIB") or _loaded_nccl_path()
+        _lib.call("ctx_comm_load", path.encode() if path else None)
+        token = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            _lib.call("ctx_comm_unique_id", ctypes.c_void_p(token.data_ptr()))
+        carrier = token.to(device) if dist.get_backend(group) == "nccl" else token
+        dist.broadcast(carrier, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        token = carrier.cpu().contiguous()
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _lib.call("ctx_comm_init", ctypes.c_void_p(ctypes.addressof(handle)), world_size, ctypes.c_void_p(token.data_ptr()), rank)
+        self.handle, self.device, self.world_size = handle, torch.device(device), world_size
+        self.version = _lib.lib().ctx_comm_version()
+
+    def all_reduce(self, t: torch.Tensor):
+        """In-place sum of a contiguous fp32 CUDA tensor over the ranks, on the current stream of its device."""
+        if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.device == self.device):
+            raise self._lib.CtxNerfError("BucketComm.all_reduce: contiguous fp32 tensor on the communicator's device")
+        self._lib.call("ctx_allreduce", self.handle, self._lib.ptr(t), t.numel(), self._lib.stream_ptr(self.device))
+
+    def close(self):
+        if self.handle is not None and self.handle.value:
+            torch.cuda.synchronize(self.device)
+            self._lib.call("ctx_comm_destroy", self.handle)
+        self.handle = None
+
+
 def shard_rays(n_total: int, rank: int, world_size: int):
     """Contiguous ray range [lo, hi) of this rank (inference: row blocks of the
     image; any remainder goes to the first ranks)."""
@@ -64,6 +121,13 @@ def rank_generator(seed: int, rank: int, device="cpu") -> torch.Generator:
     g = torch.Generator(device=device)
     g.manual_seed(seed + rank)
     return g
+
+
+def dist_backend():
+    """Backend name of the default process group ("" when there is none)."""
+    if dist.is_available() and dist.is_initialized():
+        return str(dist.get_backend())
+    return ""
 
 
 def world():

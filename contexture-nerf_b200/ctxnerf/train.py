@@ -25,7 +25,7 @@ import torch
 
 from . import _lib, ops
 from ._lib import CtxNerfError, call, ptr, stream_ptr
-from .dist import FlatBucket, world
+from .dist import BucketComm, FlatBucket, dist_backend, world
 from .mlp import TILE, forward_raw, pack_into
 from .mlp_bwd import wgrad_scratch
 from .run_nerf_helpers import NeRF
@@ -93,6 +93,11 @@ class NerfTrainer:
         self.exp_avg = torch.zeros_like(self.bucket.flat)
         self.exp_avg_sq = torch.zeros_like(self.bucket.flat)
         self.rank, self.world_size = world()
+        # gradient all-reduce through the library's own NCCL binding (ctx_allreduce on the step's stream: the whole
+        # step is then one graph); CTXNERF_NCCL=0 or a non-NCCL process group -> torch.distributed between two graphs
+        self.comm = None
+        if self.world_size > 1 and os.environ.get("CTXNERF_NCCL", "1") != "0" and dist_backend() == "nccl":
+            self.comm = BucketComm(dev)
         self._loss = torch.zeros(1, device=dev)
         # device-side step state: [0] Philox seed offset, [1] Adam step count (ctx_step_tick advances both)
         self._ctr = torch.zeros(2, device=dev, dtype=torch.int64)
@@ -288,8 +293,14 @@ class NerfTrainer:
             self._run(pl, optimizer_step)
         return self._loss
 
+    def _all_reduce(self):
+        if self.comm is not None:
+            self.comm.all_reduce(self.bucket.grad)
+        else:
+            self.bucket.all_reduce()
+
     def _run(self, pl: _Plan, optimizer_step: bool):
-        multi = self.world_size > 1
+        multi = self.world_size > 1 and self.comm is None      # all-reduce outside the graph (torch.distributed)
         if optimizer_step:     # the modules' own pack caches (direct net(x) calls) do not see the in-place Adam update
             self.coarse._packed.invalidate()
             self.fine._packed.invalidate()
@@ -298,7 +309,7 @@ class NerfTrainer:
             # eager launch sequence (first step of a batch size: sets the kernels' attributes; timed passes)
             l0 = _lib.launch_count
             self._enqueue_head(pl)
-            self.bucket.all_reduce()
+            self._all_reduce()
             if optimizer_step:
                 self._enqueue_tail()
             if graphable:
@@ -314,7 +325,8 @@ class NerfTrainer:
             pl.graph_tail.replay()
 
     def _capture(self, pl: _Plan, multi: bool):
-        """Capture the step into one CUDA graph (single process) or two with the all-reduce between them."""
+        """Capture the step into one CUDA graph (single process, or N processes with the library's NCCL binding: the
+        all-reduce is a node of the graph) or two with torch.distributed's all-reduce between them."""
         dev = self.device
         torch.cuda.synchronize(dev)
         saved = _lib.launch_count
@@ -323,6 +335,8 @@ class NerfTrainer:
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self._enqueue_head(pl)
                 if not multi:
+                    if self.comm is not None:
+                        self.comm.all_reduce(self.bucket.grad)
                     self._enqueue_tail()
             tail = None
             if multi:

@@ -23,9 +23,10 @@
 extern "C" {
 #endif
 
-#define CTXNERF_ABI_VERSION 2
+#define CTXNERF_ABI_VERSION 3
 #define CTX_ERR_BAD_ARG (-1)
 #define CTX_ERR_UNSUPPORTED (-2)
+#define CTX_ERR_NO_NCCL (-3)
 
 int ctx_abi_version(void);
 /* static string for a code returned by any ctx_* call */
@@ -239,6 +240,22 @@ int ctx_view_weight_masks(const float* face_normals, const int64_t* face_idx, in
 int64_t ctx_face_view_map_blocks(int64_t n_pixels);
 int ctx_face_view_map(const int64_t* face_idx, int V, int H, int W, int64_t* block_counts, int64_t* rows, int pass,
                       void* stream);
+
+/* ---- gradient all-reduce: the one exchange step of the ray-sharded training step, replacing the
+ * reduce-add of nn.DataParallel (src/training/trainer.py:134-135).  NCCL is opened at run time (dlopen; `path`
+ * nullable = "libnccl.so.2" by soname), so the library has no link-time dependency on it; every call below returns
+ * CTX_ERR_NO_NCCL (text in ctx_comm_last_error) when NCCL is absent or reports an error.  The communicator is an
+ * opaque handle owned by the caller.  Rendezvous: one rank makes the 128-byte token with ctx_comm_unique_id and the
+ * host passes it to the others; ctx_comm_init is collective and binds to the CURRENT device.  ctx_allreduce sums
+ * bucket[0..n) in place on `stream`; it can be captured into a CUDA graph (all ranks capture the same sequence).  */
+#define CTX_COMM_ID_BYTES 128
+int ctx_comm_load(const char* path);
+int ctx_comm_version(void);
+const char* ctx_comm_last_error(void);
+int ctx_comm_unique_id(void* id_out_host);
+int ctx_comm_init(void** comm_out, int n_ranks, const void* id_host, int rank);
+int ctx_comm_destroy(void* comm);
+int ctx_allreduce(void* comm, float* bucket, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

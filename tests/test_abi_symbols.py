@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 from conftest import ROOT
 
 
@@ -30,7 +32,7 @@ def test_library_exports_every_declared_symbol(libpath):
 def test_python_binding_covers_header(libpath):
     from ctxnerf import _lib
     assert set(declared_symbols()) <= set(_lib._SIGNATURES), set(declared_symbols()) - set(_lib._SIGNATURES)
-    assert _lib.lib().ctx_abi_version() == 2
+    assert _lib.lib().ctx_abi_version() == 3
     assert b"bad argument" in _lib.lib().ctx_error_string(-1)
 
 
@@ -43,6 +45,41 @@ def test_argument_errors_do_not_need_a_gpu(libpath):
     assert lib.ctx_posenc_fwd(None, None, -1, 3, 10, 1, 1, None) == -1
     assert lib.ctx_resample_fwd(None, 0, 0, None, 0, None, None, 1, 0, None, 8, 1, 16, None, None, None, 0, 0,
                                 None, None) == -1
+
+
+def test_communicator_binding_loads_nccl_at_run_time(libpath):
+    """ctx_comm_*: no link-time dependency on NCCL (the library must load without it), a clear error before
+    ctx_comm_load, and -- with the NCCL copy torch ships -- the 2.x version check.  No GPU work."""
+    import subprocess
+    deps = subprocess.run(["ldd", libpath], capture_output=True, text=True).stdout
+    assert "nccl" not in deps
+    from ctxnerf import _lib
+    lib = _lib.lib()
+    buf = ctypes.create_string_buffer(128)
+    if lib.ctx_comm_version() == 0:                     # not loaded yet in this process
+        assert lib.ctx_comm_unique_id(buf) == -3
+        assert lib.ctx_allreduce(ctypes.c_void_p(1), ctypes.c_void_p(16), 4, None) == -3
+        assert lib.ctx_comm_load(b"/nonexistent/libnccl.so.2") == -3
+        assert b"dlopen failed" in lib.ctx_comm_last_error()
+        assert b"NCCL" in lib.ctx_error_string(-3)
+    import torch                                        # (maps its bundled NCCL where the platform has one)
+    from ctxnerf.dist import _loaded_nccl_path
+    import glob
+    path = _loaded_nccl_path()
+    if path is None:
+        cands = glob.glob(os.path.join(os.path.dirname(os.path.dirname(torch.__file__)), "nvidia", "nccl", "lib",
+                                       "libnccl.so.2"))
+        path = cands[0] if cands else None
+    if path is None:
+        pytest.skip("no NCCL shared object in this environment")
+    assert lib.ctx_comm_load(path.encode()) == 0
+    assert 20000 <= lib.ctx_comm_version() < 30000
+    assert lib.ctx_comm_unique_id(None) == -1
+    assert lib.ctx_comm_init(None, 2, buf, 0) == -1
+    handle = ctypes.c_void_p()
+    assert lib.ctx_comm_init(ctypes.c_void_p(ctypes.addressof(handle)), 2, buf, 2) == -1      # rank out of range
+    assert lib.ctx_allreduce(None, None, 0, None) == -1
+    assert lib.ctx_comm_destroy(None) == 0
 
 
 def test_mlp_describe_matches_the_reference_layer_structure(libpath):

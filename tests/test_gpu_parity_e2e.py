@@ -270,13 +270,19 @@ def test_allreduced_gradients_of_two_ranks_equal_single_process_sum(cuda):
     n = torch.cuda.device_count()
     if n < 2:
         pytest.skip("needs >= 2 GPUs")
-    port = 29600 + (os.getpid() % 300)
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                        "--master-addr", "127.0.0.1", "--master-port", str(port),
-                        os.path.join(ROOT, "tools", "dist_check.py")], capture_output=True, text=True, timeout=900)
-    _diag("dist_check (2 ranks):\n" + r.stdout[-1500:])
-    assert r.returncode == 0, r.stderr[-3000:]
-    assert r.stdout.count("all-reduced vs single-process sum") == 2
+    # both routes of the all-reduce: the library's NCCL binding (ctx_allreduce, a node of the step graph) and
+    # torch.distributed between two graphs (CTXNERF_NCCL=0)
+    for k, (nccl, route) in enumerate((("1", "ctx_allreduce (NCCL"), ("0", "torch.distributed"))):
+        port = 29600 + (os.getpid() % 300) + k
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                            "--master-addr", "127.0.0.1", "--master-port", str(port),
+                            os.path.join(ROOT, "tools", "dist_check.py")], capture_output=True, text=True, timeout=900,
+                           env=dict(os.environ, CTXNERF_NCCL=nccl))
+        _diag(f"dist_check (2 ranks, CTXNERF_NCCL={nccl}):\n" + r.stdout[-1500:])
+        assert r.returncode == 0, r.stderr[-3000:]
+        assert r.stdout.count("all-reduced vs single-process sum") == 2
+        assert r.stdout.count(route) == 2
+        assert r.stdout.count("identical on all ranks: True") == 2
 
 
 def test_drop_in_mlp_survives_nn_dataparallel(cuda):

@@ -1,5 +1,7 @@
 """torchrun --nproc-per-node N tools/dist_check.py : the all-reduced gradient bucket of N ranks (each with
-its own 4096-ray batch) equals the sum of the per-batch gradients computed by one process."""
+its own 4096-ray batch) equals the sum of the per-batch gradients computed by one process; then four
+optimizer steps (the captured graph from the second on, all-reduce inside it when the library's NCCL binding is in
+use) must leave bit-identical parameters on every rank.  CTXNERF_NCCL=0 checks the torch.distributed route."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "contexture-nerf_b200")]
@@ -22,21 +24,33 @@ for r in range(world):
 tr.step(*batches[rank], optimizer_step=False)
 reduced = tr.bucket.grad.clone()
 # single process reference on this rank: sum of the gradients of every batch
-tr.world_size_backup = None
 ref = torch.zeros_like(reduced)
 for b in batches:
     tr.bucket.zero_grad()
-    f = None
-    import ctxnerf.dist as cd
-    saved = cd.FlatBucket.all_reduce
-    cd.FlatBucket.all_reduce = lambda self, group=None, async_op=False: None
+    saved = tr._all_reduce
+    tr._all_reduce = lambda: None
     tr.step(*b, optimizer_step=False)
-    cd.FlatBucket.all_reduce = saved
+    tr._all_reduce = saved
     ref += tr.bucket.grad
 torch.cuda.synchronize()
 err = (reduced - ref).abs().max().item() / ref.abs().max().item()
 cos = torch.nn.functional.cosine_similarity(reduced, ref, dim=0).item()
-print(f"rank {rank}/{world}: all-reduced vs single-process sum: max rel err {err:.3e}, cosine {cos:.8f}", flush=True)
+route = f"ctx_allreduce (NCCL {tr.comm.version})" if tr.comm is not None else "torch.distributed"
+print(f"rank {rank}/{world}: all-reduced vs single-process sum: max rel err {err:.3e}, cosine {cos:.8f} [{route}]",
+      flush=True)
 assert err < 1e-3 and cos > 0.999999
+# optimizer steps: eager, then captured; every rank must hold the same parameters afterwards
+tr.bucket.zero_grad()
+for i in range(4):
+    loss = tr.step(*batches[(rank + i) % world])
+torch.cuda.synchronize()
+mine = tr.bucket.flat.clone()
+everyone = [torch.empty_like(mine) for _ in range(world)]
+dist.all_gather(everyone, mine)
+same = all(torch.equal(e, mine) for e in everyone)
+graphs = sum(pl.graph is not None for pl in tr._plans.values()), sum(pl.graph_tail is not None for pl in tr._plans.values())
+print(f"rank {rank}/{world}: parameters after 4 steps identical on all ranks: {same}; loss {loss.item():.5f}; "
+      f"graphs head/tail {graphs}", flush=True)
+assert same and torch.isfinite(loss).all()
 dist.barrier()
 dist.destroy_process_group()
