@@ -481,7 +481,9 @@ def main():
             * RAYS_PER_GPU * EVALS_PER_RAY / (ms / args.steps * 1e-3) / 1e9 / pk["hbm_gbs"],
             "kernels": kernels, "final_loss": final_loss, "sustained": sustained}
     if world > 1:
-        line["allreduce"] = {"route": "ctx_allreduce (libctxnerf NCCL binding, inside the step graph)" if tr.comm is not None
+        line["allreduce"] = {"route": ("ctx_allreduce (libctxnerf NCCL binding, inside the step graph"
+                                       + (", fine half beside the coarse backward chain)" if tr.split_reduce else ")"))
+                             if tr.comm is not None
                              else "torch.distributed between two graphs",
                              "nccl_version": tr.comm.version if tr.comm is not None else None,
                              "bytes": 4 * tr.bucket.numel}

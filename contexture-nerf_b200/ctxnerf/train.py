@@ -65,6 +65,7 @@ class _Plan:
         self.graph_tail = None     # second graph (Adam + re-pack) when the all-reduce runs between the two
         self.eager_steps = 0
         self.kernels_per_step = 0
+        self.fine_reduced = False  # the head has already all-reduced the fine network's half of the bucket
 
 
 class NerfTrainer:
@@ -98,6 +99,12 @@ class NerfTrainer:
         self.comm = None
         if self.world_size > 1 and os.environ.get("CTXNERF_NCCL", "1") != "0" and dist_backend() == "nccl":
             self.comm = BucketComm(dev)
+        self.reduce_gradients = True       # (tools/dist_check.py turns the exchange off for its single-process sums)
+        # with the library's binding the bucket goes in two halves: the fine network's right behind its wgrad, beside
+        # the coarse chain still running on the side stream, the coarse network's after the join (CTXNERF_SPLIT_REDUCE=0:
+        # one all-reduce of the whole bucket after the join)
+        self._n_coarse = sum(p.numel() for p in self.coarse.parameters())
+        self.split_reduce = self.comm is not None and os.environ.get("CTXNERF_SPLIT_REDUCE", "1") != "0"
         self._loss = torch.zeros(1, device=dev)
         # device-side step state: [0] Philox seed offset, [1] Adam step count (ctx_step_tick advances both)
         self._ctr = torch.zeros(2, device=dev, dtype=torch.int64)
@@ -195,6 +202,7 @@ class NerfTrainer:
         jit = self.perturb > 0.0
         main = torch.cuda.current_stream(dev)
         early = self.overlap_backward and self.early_coarse
+        pl.fine_reduced = False
         call("ctx_step_tick", ptr(self._ctr), ptr(self._loss), stream_ptr(dev))
         self.bucket.zero_grad()
         ops.raygen(self.H, self.W, self.K, self.c2w, ray_idx=pl.idx, n_samples=S, near=self.near, far=self.far,
@@ -248,6 +256,9 @@ class NerfTrainer:
                 self._ev1.record(self._side)
             self._timed("mlp_wgrad_fine", lambda: self._wgrad(self.fine, pl.acts_f, pl.dacts_f, Pf,
                                                               max_sms=self.n_sms - self.side_sms))
+            if self.split_reduce and self.reduce_gradients:
+                self.comm.all_reduce(self.bucket.grad[self._n_coarse:])
+                pl.fine_reduced = True
             main.wait_event(self._ev1)
             if self.timers is not None:   # span of the concurrent group on the main stream
                 g1 = torch.cuda.Event(enable_timing=True)
@@ -293,9 +304,12 @@ class NerfTrainer:
             self._run(pl, optimizer_step)
         return self._loss
 
-    def _all_reduce(self):
+    def _all_reduce(self, pl: _Plan):
+        """The exchange step after the join of the two backward chains (what the head has not already reduced)."""
+        if not self.reduce_gradients:
+            return
         if self.comm is not None:
-            self.comm.all_reduce(self.bucket.grad)
+            self.comm.all_reduce(self.bucket.grad[:self._n_coarse] if pl.fine_reduced else self.bucket.grad)
         else:
             self.bucket.all_reduce()
 
@@ -309,7 +323,7 @@ class NerfTrainer:
             # eager launch sequence (first step of a batch size: sets the kernels' attributes; timed passes)
             l0 = _lib.launch_count
             self._enqueue_head(pl)
-            self._all_reduce()
+            self._all_reduce(pl)
             if optimizer_step:
                 self._enqueue_tail()
             if graphable:
@@ -321,7 +335,7 @@ class NerfTrainer:
         _lib.launch_count += pl.kernels_per_step
         pl.graph.replay()
         if multi:
-            self.bucket.all_reduce()
+            self._all_reduce(pl)
             pl.graph_tail.replay()
 
     def _capture(self, pl: _Plan, multi: bool):
@@ -335,8 +349,7 @@ class NerfTrainer:
             with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 self._enqueue_head(pl)
                 if not multi:
-                    if self.comm is not None:
-                        self.comm.all_reduce(self.bucket.grad)
+                    self._all_reduce(pl)
                     self._enqueue_tail()
             tail = None
             if multi:
