@@ -238,6 +238,9 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
       ex[k] = ok ? t.expo : 1.0f;            // padded samples: alpha = 0, t = 1 + 1e-10 ~ identity (masked below)
       pref[k] = run;
       run *= ok ? t.trans_factor : 1.0f;
+      // the colour logits are only ever used through their sigmoid: replace them in place, once (the forward sums,
+      // G_k and the final gradients below then cost no further exp / division)
+      rw[k].x = sigmoidf_(rw[k].x); rw[k].y = sigmoidf_(rw[k].y); rw[k].z = sigmoidf_(rw[k].z);
     }
     const float incl = group_scan_prod<G>(run, lane);
     float excl = __shfl_up_sync(CTX_FULL_MASK, incl, 1, G);
@@ -251,9 +254,9 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
       for (int k = 0; k < K; ++k) {
         wk[k] = (1.0f - ex[k]) * (excl * pref[k]);
         if (s0 + k < S) {
-          sr += wk[k] * sigmoidf_(rw[k].x);
-          sg += wk[k] * sigmoidf_(rw[k].y);
-          sb += wk[k] * sigmoidf_(rw[k].z);
+          sr += wk[k] * rw[k].x;
+          sg += wk[k] * rw[k].y;
+          sb += wk[k] * rw[k].z;
           sa += wk[k];
         } else {
           wk[k] = 0.f;
@@ -305,7 +308,7 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
 #pragma unroll
     for (int k = K - 1; k >= 0; --k) {
       const bool ok = s0 + k < S;
-      const float cr = sigmoidf_(rw[k].x), cg = sigmoidf_(rw[k].y), cb = sigmoidf_(rw[k].z);
+      const float cr = rw[k].x, cg = rw[k].y, cb = rw[k].z;
       Gs[k] = gw[k] + gr * cr + gg * cg + gb * cb + gd * zl[k] + ga;
       const float alpha = 1.0f - ex[k];
       const float a = ok ? ((1.0f - alpha) + 1e-10f) : 1.0f;
@@ -331,7 +334,7 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
       const float alpha = 1.0f - ex[k];
       const float T = excl * pref[k];
       if (ok) {
-        const float cr = sigmoidf_(rw[k].x), cg = sigmoidf_(rw[k].y), cb = sigmoidf_(rw[k].z);
+        const float cr = rw[k].x, cg = rw[k].y, cb = rw[k].z;
         const float g_alpha = T * (Gs[k] - U);
         const float sig = rw[k].w + nz[k];
         const float g_sigma = (sig > 0.f) ? g_alpha * ex[k] * dist[k] : 0.f;
