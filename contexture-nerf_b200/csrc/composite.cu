@@ -25,7 +25,16 @@ struct SampleTerms {
   float alpha, trans_factor, expo;  // expo = exp(-relu(sigma)*dist) ; trans_factor = 1-alpha+1e-10
 };
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+// sigmoid: 1 / (1 + e^-x) with the reciprocal as MUFU.RCP + one Newton step (error < 1 ulp, like the oracle's own
+// exp).  The IEEE division the compiler emits for 1.0f / y carries a range check, a branch and a slow-path CALL per
+// use -- with three sigmoids per sample that was a quarter of the kernels' instructions, and they are issue-bound.
+// y is clamped to <= 1e30 so that the Newton step never sees inf * 0 (sigmoid(x) for x < -69 is then 1e-30, not e^x).
+__device__ __forceinline__ float sigmoidf_(float x) {
+  const float y = 1.0f + fminf(expf(-x), 1e30f);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
+  return fmaf(r, fmaf(-y, r, 1.0f), r);
+}
 
 __device__ __forceinline__ SampleTerms sample_terms(float sigma, float dist) {
   SampleTerms t;
