@@ -30,7 +30,7 @@ struct SampleTerms {
 // use -- with three sigmoids per sample that was a quarter of the kernels' instructions, and they are issue-bound.
 // y is clamped to <= 1e30 so that the Newton step never sees inf * 0 (sigmoid(x) for x < -69 is then 1e-30, not e^x).
 __device__ __forceinline__ float sigmoidf_(float x) {
-  const float y = 1.0f + fminf(expf(-x), 1e30f);
+  const float y = 1.0f + fminf(__expf(-x), 1e30f);     // ex2.approx: |d sigmoid| <= s (1 - s) (2.4e-7 + 6e-8 |x|) < 1 ulp of 0.5
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
   return fmaf(r, fmaf(-y, r, 1.0f), r);
@@ -106,7 +106,7 @@ __device__ __forceinline__ void store_row(float* __restrict__ p, int64_t base, i
 // G lanes share a ray (32 / G rays per warp): short rays use 8- or 16-lane groups so that the scan and the five
 // reductions, the part of the work that does not shrink with S, are paid once per 4 or 2 rays.
 template <int K, int G>
-__global__ void __launch_bounds__(kCompWarps * 32)
+__global__ void __launch_bounds__(kCompWarps * 32, K <= 4 ? 4 : (K <= 8 ? 3 : (K <= 12 ? 2 : 1)))
 composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z,
                      const float* __restrict__ rays_d, const float* __restrict__ noise,
                      int64_t R, int S_all, int vec, int white_bkgd,
@@ -196,7 +196,7 @@ composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
 // composite_fwd + mse + composite_bwd.  It writes g_raw, optionally weights (the coarse pass feeds sample_pdf) and
 // rgb_map, and adds sum((rgb-target)^2) * loss_scale into loss[0] (one atomic per warp pass).
 template <int K, int G, bool TRAIN>
-__global__ void __launch_bounds__(kCompWarps * 32)
+__global__ void __launch_bounds__(kCompWarps * 32, K <= 4 ? 3 : (K <= 8 ? 2 : 1))
 composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z,
                      const float* __restrict__ rays_d, const float* __restrict__ noise,
                      int64_t R, int S_all, int vec, int white_bkgd,

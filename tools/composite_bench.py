@@ -11,7 +11,8 @@ def timeit(fn, n=10):
     torch.cuda.synchronize(); a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); [fn() for _ in range(n)]; b.record(); torch.cuda.synchronize(); return a.elapsed_time(b) / n * 1e-3
 R = 1 << (19 if "--small" in sys.argv else 20)
-for S in (32, 64, 128, 192, 256, 384, 512):
+S_LIST = [int(a) for a in sys.argv[1:] if a.isdigit()] or [32, 64, 128, 192, 256, 384, 512]
+for S in S_LIST:
     raw = torch.randn(R, S, 4, device=dev); raw[..., 3] *= 5
     z = torch.sort(torch.rand(R, S, device=dev) * 4 + 2, -1)[0]; d = torch.randn(R, 3, device=dev)
     rr = raw.clone().requires_grad_(True); outs = ops.composite(rr, z, d)
