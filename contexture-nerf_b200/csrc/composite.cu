@@ -371,19 +371,26 @@ composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
 // where 16 samples per lane cost more registers than the second pass over a chunk costs time.
 constexpr int kCompMaxChunks = 64;      // per-chunk entry transmittances kept in shared memory by the backward
 
+// widest aligned vector access (floats) for rows of S floats behind the given pointers (device-side twin of comp_vec)
+__device__ __forceinline__ int dev_vec(int S, const void* a, const void* b, const void* c) {
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c);
+  return ((S & 3) == 0 && (bits & 15) == 0) ? 4 : 1;
+}
+
 template <int K>
 __device__ __forceinline__ void chunk_load(const float4* __restrict__ raw, const float* __restrict__ z,
                                            const float* __restrict__ noise, int64_t base, int c0, int lane, int S,
-                                           float dnorm, float4 (&rw)[K], float (&zl)[K + 1], float (&sig)[K],
+                                           int vec, float dnorm, float4 (&rw)[K], float (&zl)[K + 1], float (&sig)[K],
                                            float (&dist)[K]) {
   const int s0 = c0 + lane * K;
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const int s = s0 + k;
-    rw[k] = (s < S) ? __ldg(raw + base + s) : make_float4(0.f, 0.f, 0.f, 0.f);
-    zl[k] = (s < S) ? __ldg(z + base + s) : 0.f;
-    sig[k] = rw[k].w + ((noise != nullptr && s < S) ? __ldg(noise + base + s) : 0.f);
-  }
+  for (int k = 0; k < K; ++k)
+    rw[k] = (s0 + k < S) ? __ldg(raw + base + s0 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+  load_row<K>(z, base, s0, S, vec, zl);                        // 16-byte pieces when the rows allow it
+  float nz[K + 1];
+  if (noise != nullptr) load_row<K>(noise, base, s0, S, vec, nz);
+#pragma unroll
+  for (int k = 0; k < K; ++k) sig[k] = rw[k].w + (noise != nullptr ? nz[k] : 0.f);
   zl[K] = (s0 + K < S) ? __ldg(z + base + s0 + K) : 0.f;     // first depth of the next lane / next chunk
 #pragma unroll
   for (int k = 0; k < K; ++k) {
@@ -401,6 +408,7 @@ composite_chunked_fwd_kernel(const float4* __restrict__ raw, const float* __rest
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (int64_t)blockIdx.x * kCompWarps + (threadIdx.x >> 5);
   const int64_t nwarps = (int64_t)gridDim.x * kCompWarps;
+  const int vec = dev_vec(S, z, noise, weights);
   for (int64_t ray = warp0; ray < R; ray += nwarps) {
     const float dx = rays_d[ray * 3 + 0], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
     const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
@@ -409,7 +417,7 @@ composite_chunked_fwd_kernel(const float4* __restrict__ raw, const float* __rest
     for (int c0 = 0; c0 < S; c0 += 32 * K) {
       float4 rw[K];
       float zl[K + 1], sig[K], dist[K];
-      chunk_load<K>(raw, z, noise, base, c0, lane, S, dnorm, rw, zl, sig, dist);
+      chunk_load<K>(raw, z, noise, base, c0, lane, S, vec, dnorm, rw, zl, sig, dist);
       float al[K], pref[K];
       float run = 1.0f;
 #pragma unroll
@@ -423,16 +431,19 @@ composite_chunked_fwd_kernel(const float4* __restrict__ raw, const float* __rest
       const float incl = group_scan_prod<32>(run, lane);
       float excl = __shfl_up_sync(CTX_FULL_MASK, incl, 1);
       if (lane == 0) excl = 1.0f;
+      float wv[K];
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const int s = c0 + lane * K + k;
+        wv[k] = 0.f;
         if (s < S) {
           const float w = al[k] * ((carry * excl) * pref[k]);
-          weights[base + s] = w;
+          wv[k] = w;
           sr += w * sigmoidf_(rw[k].x); sg += w * sigmoidf_(rw[k].y); sb += w * sigmoidf_(rw[k].z);
           sd += w * zl[k]; sa += w;
         }
       }
+      store_row<K>(weights, base, c0 + lane * K, S, vec, wv);
       carry *= __shfl_sync(CTX_FULL_MASK, incl, 31);
     }
     sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sd = warp_sum(sd); sa = warp_sum(sa);
@@ -462,6 +473,7 @@ composite_chunked_bwd_kernel(const float4* __restrict__ raw, const float* __rest
   const int64_t warp0 = (int64_t)blockIdx.x * kCompWarps + wib;
   const int64_t nwarps = (int64_t)gridDim.x * kCompWarps;
   const int n_chunks = (S + 32 * K - 1) / (32 * K);
+  const int vec = dev_vec(S, z, noise, TRAIN ? (const void*)weights_out : (const void*)g_weights);
   float loss_acc = 0.f;
   for (int64_t ray = warp0; ray < R; ray += nwarps) {
     const float dx = rays_d[ray * 3 + 0], dy = rays_d[ray * 3 + 1], dz = rays_d[ray * 3 + 2];
@@ -473,7 +485,7 @@ composite_chunked_bwd_kernel(const float4* __restrict__ raw, const float* __rest
       const int c0 = ci * 32 * K;
       float4 rw[K];
       float zl[K + 1], sig[K], dist[K];
-      chunk_load<K>(raw, z, noise, base, c0, lane, S, dnorm, rw, zl, sig, dist);
+      chunk_load<K>(raw, z, noise, base, c0, lane, S, vec, dnorm, rw, zl, sig, dist);
       if (lane == 0) s_carry[wib][ci] = carry;
       float al[K], pref[K];
       float run = 1.0f;
@@ -488,16 +500,19 @@ composite_chunked_bwd_kernel(const float4* __restrict__ raw, const float* __rest
       const float incl = group_scan_prod<32>(run, lane);
       float excl = __shfl_up_sync(CTX_FULL_MASK, incl, 1);
       if (lane == 0) excl = 1.0f;
+      float wv[K];
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         const int s = c0 + lane * K + k;
+        wv[k] = 0.f;
         if (s < S) {
           const float w = al[k] * ((carry * excl) * pref[k]);
-          if (TRAIN && weights_out != nullptr) weights_out[base + s] = w;
+          wv[k] = w;
           if (TRAIN) { sr += w * sigmoidf_(rw[k].x); sg += w * sigmoidf_(rw[k].y); sb += w * sigmoidf_(rw[k].z); }
           sd += w * zl[k]; sa += w;
         }
       }
+      if (TRAIN && weights_out != nullptr) store_row<K>(weights_out, base, c0 + lane * K, S, vec, wv);
       carry *= __shfl_sync(CTX_FULL_MASK, incl, 31);
     }
     sd = warp_sum(sd); sa = warp_sum(sa);
@@ -536,7 +551,7 @@ composite_chunked_bwd_kernel(const float4* __restrict__ raw, const float* __rest
       const int c0 = ci * 32 * K;
       float4 rw[K];
       float zl[K + 1], sig[K], dist[K];
-      chunk_load<K>(raw, z, noise, base, c0, lane, S, dnorm, rw, zl, sig, dist);
+      chunk_load<K>(raw, z, noise, base, c0, lane, S, vec, dnorm, rw, zl, sig, dist);
       const float cin = s_carry[wib][ci];
       float ex[K], pref[K], Gs[K];
       float run = 1.0f;
@@ -553,12 +568,14 @@ composite_chunked_bwd_kernel(const float4* __restrict__ raw, const float* __rest
       if (lane == 0) excl = 1.0f;
       // the lane's composed map  U_first = Bc + A * U_(first sample of the next lane)
       float A = 1.0f, Bc = 0.f;
+      float gwv[K + 1];
+      if (!TRAIN && g_weights != nullptr) load_row<K>(g_weights, base, c0 + lane * K, S, vec, gwv);
 #pragma unroll
       for (int k = K - 1; k >= 0; --k) {
         const int s = c0 + lane * K + k;
         const bool ok = s < S;
         const float cr = sigmoidf_(rw[k].x), cg = sigmoidf_(rw[k].y), cb = sigmoidf_(rw[k].z);
-        const float gw = (!TRAIN && g_weights != nullptr && ok) ? __ldg(g_weights + base + s) : 0.f;
+        const float gw = (!TRAIN && g_weights != nullptr && ok) ? gwv[k] : 0.f;
         Gs[k] = gw + gr * cr + gg * cg + gb * cb + gd * zl[k] + ga;
         const float alpha = 1.0f - ex[k];
         const float a = ok ? ((1.0f - alpha) + 1e-10f) : 1.0f;
