@@ -60,6 +60,8 @@ _SIGNATURES = {
     "ctx_step_tick": (c_int, [P, P, P]),
     "ctx_adam_step_dev": (c_int, [P, P, P, P, c_int64, c_float, c_float, c_float, c_float, P, c_float, c_float, P]),
     "ctx_mse_fwd_bwd": (c_int, [P, P, P, c_int64, c_float, P, P, P, P]),
+    "ctx_render_rays": (c_int, [P, P]),
+    "ctx_render_args_bytes": (c_int, []),
     "ctx_comm_load": (c_int, [ctypes.c_char_p]),
     "ctx_comm_version": (c_int, []),
     "ctx_comm_last_error": (ctypes.c_char_p, []),
@@ -68,6 +70,24 @@ _SIGNATURES = {
     "ctx_comm_destroy": (c_int, [P]),
     "ctx_allreduce": (c_int, [P, P, c_int64, P]),
 }
+
+
+class CtxNet(ctypes.Structure):
+    """CtxNet of include/ctxnerf.h"""
+    _fields_ = [("desc", c_void_p), ("wpacked", c_void_p), ("fparams", c_void_p)]
+
+
+class CtxRenderArgs(ctypes.Structure):
+    """CtxRenderArgs of include/ctxnerf.h (field for field; ctx_render_args_bytes() checks the layout)"""
+    _fields_ = ([("H", c_int), ("W", c_int), ("fx", c_float), ("fy", c_float), ("cx", c_float), ("cy", c_float),
+                 ("c2w", c_void_p), ("c2w_ld", c_int), ("ray_idx", c_void_p), ("n_rays", c_int64),
+                 ("near", c_float), ("far", c_float), ("lindisp", c_int), ("perturb", c_int), ("seed", c_uint64),
+                 ("seed_dev", c_void_p), ("sphere", c_void_p), ("n_samples", c_int), ("n_importance", c_int),
+                 ("white_bkgd", c_int), ("L_pts", c_int), ("L_dirs", c_int), ("max_sms", c_int),
+                 ("coarse", CtxNet), ("fine", CtxNet)]
+                + [(n, c_void_p) for n in ("rays_o", "rays_d", "viewdirs", "z_coarse", "raw_coarse", "weights_coarse",
+                                           "z_samples", "z_fine", "raw_fine", "weights_fine", "rgb0", "disp0", "acc0",
+                                           "depth0", "rgb_map", "disp_map", "acc_map", "depth_map")])
 
 
 # diagnostics build (libctxnerf_diag.so, include/ctxnerf_diag.h): tools/ and one GPU test only
@@ -136,7 +156,7 @@ def check(code: int, what: str) -> None:
 
 
 # kernels launched per ABI call (bench.py reports the total as gpu_launches)
-KERNELS_PER_CALL = {"ctx_mlp_bwd": 2, "ctx_allreduce": 0, "ctx_comm_load": 0, "ctx_comm_unique_id": 0, "ctx_comm_init": 0, "ctx_comm_destroy": 0}     # (the view-direction wgrad also runs a small post kernel: +1, counted by the callers that know the net)
+KERNELS_PER_CALL = {"ctx_mlp_bwd": 2, "ctx_render_rays": 6, "ctx_allreduce": 0, "ctx_comm_load": 0, "ctx_comm_unique_id": 0, "ctx_comm_init": 0, "ctx_comm_destroy": 0}     # (the view-direction wgrad also runs a small post kernel: +1, counted by the callers that know the net)
 launch_count = 0
 
 

@@ -385,21 +385,44 @@ class NerfTrainer:
     # ------------------------------------------------------------ inference
     def _render(self, ray_idx, perturb, seed=0, max_sms=0):
         """Forward-only coarse+fine render of the given pixels (None = the whole image): dynamic shapes, fresh
-        outputs; shares the trainer's packed weights."""
+        outputs; shares the trainer's packed weights.  ONE C-ABI call: ctx_render_rays (csrc/render.cu) enqueues
+        raygen -> MLP -> raw2outputs -> sample_pdf + merge -> MLP -> raw2outputs."""
         dev, S, Ni = self.device, self.N_samples, self.N_importance
-        jit = bool(perturb)
-        r = ops.raygen(self.H, self.W, self.K, self.c2w, ray_idx=ray_idx, n_samples=S, near=self.near, far=self.far,
-                       lindisp=self.lindisp, perturb=jit, seed=seed, want_viewdirs=True)
-        o, d, v, z_c = r["rays_o"], r["rays_d"], r["viewdirs"], r["z_vals"]
-        R = o.shape[0]
-        raw_c = torch.empty(R * S, 4, device=dev)
-        self._fwd(self.coarse, (o, d, v, z_c), R * S, raw_c, None, max_sms)
-        comp_c = self._composite(raw_c, z_c, d, R, S)
-        zs, z_f = ops.resample_merge(z_c, comp_c[3], Ni, det=not jit, seed=seed + 1)
-        raw_f = torch.empty(R * (S + Ni), 4, device=dev)
-        self._fwd(self.fine, (o, d, v, z_f), R * (S + Ni), raw_f, None, max_sms)
-        comp_f = self._composite(raw_f, z_f, d, R, S + Ni)
-        return dict(comp_c=comp_c, comp_f=comp_f, z_f=z_f, raw_f=raw_f, R=R)
+        if ray_idx is not None:
+            ray_idx = ray_idx.to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
+        R = self.H * self.W if ray_idx is None else ray_idx.numel()
+        f32 = dict(device=dev, dtype=torch.float32)
+        o, d, v = (torch.empty(R, 3, **f32) for _ in range(3))
+        z_c, raw_c, w_c = torch.empty(R, S, **f32), torch.empty(R * S, 4, **f32), torch.empty(R, S, **f32)
+        zs, z_f = torch.empty(R, Ni, **f32), torch.empty(R, S + Ni, **f32)
+        raw_f, w_f = torch.empty(R * (S + Ni), 4, **f32), torch.empty(R, S + Ni, **f32)
+        maps_c = [torch.empty(R, 3, **f32)] + [torch.empty(R, **f32) for _ in range(3)]     # rgb, disp, acc, depth
+        maps_f = [torch.empty(R, 3, **f32)] + [torch.empty(R, **f32) for _ in range(3)]
+        if R == 0:
+            return dict(comp_c=(maps_c[0], maps_c[1], maps_c[2], w_c, maps_c[3]),
+                        comp_f=(maps_f[0], maps_f[1], maps_f[2], w_f, maps_f[3]), z_f=z_f, raw_f=raw_f, R=0)
+        a = _lib.CtxRenderArgs()
+        a.H, a.W = self.H, self.W
+        a.fx, a.fy, a.cx, a.cy = (float(self.K[0][0]), float(self.K[1][1]), float(self.K[0][2]), float(self.K[1][2]))
+        a.c2w, a.c2w_ld = self.c2w.data_ptr(), self.c2w.stride(0)
+        a.ray_idx, a.n_rays = (None if ray_idx is None else ray_idx.data_ptr()), R
+        a.near, a.far, a.lindisp, a.perturb = self.near, self.far, int(self.lindisp), int(bool(perturb))
+        a.seed, a.seed_dev, a.sphere = int(seed), None, None
+        a.n_samples, a.n_importance, a.white_bkgd = S, Ni, int(self.white_bkgd)
+        a.L_pts, a.L_dirs, a.max_sms = self.coarse.L_pts, self.coarse.L_dirs, int(max_sms)
+        for field, net in (("coarse", self.coarse), ("fine", self.fine)):
+            w, _, f = self._pk[net]
+            cn = getattr(a, field)
+            cn.desc, cn.wpacked, cn.fparams = ctypes.addressof(net._desc.blob), w.data_ptr(), f.data_ptr()
+        for name, t in (("rays_o", o), ("rays_d", d), ("viewdirs", v), ("z_coarse", z_c), ("raw_coarse", raw_c),
+                        ("weights_coarse", w_c), ("z_samples", zs), ("z_fine", z_f), ("raw_fine", raw_f),
+                        ("weights_fine", w_f), ("rgb0", maps_c[0]), ("disp0", maps_c[1]), ("acc0", maps_c[2]),
+                        ("depth0", maps_c[3]), ("rgb_map", maps_f[0]), ("disp_map", maps_f[1]), ("acc_map", maps_f[2]),
+                        ("depth_map", maps_f[3])):
+            setattr(a, name, t.data_ptr())
+        call("ctx_render_rays", ctypes.byref(a), stream_ptr(dev))
+        return dict(comp_c=(maps_c[0], maps_c[1], maps_c[2], w_c, maps_c[3]),
+                    comp_f=(maps_f[0], maps_f[1], maps_f[2], w_f, maps_f[3]), z_f=z_f, raw_f=raw_f, R=R)
 
     def _composite(self, raw, z, d, R, S):
         dev = self.device

@@ -241,6 +241,44 @@ int64_t ctx_face_view_map_blocks(int64_t n_pixels);
 int ctx_face_view_map(const int64_t* face_idx, int V, int H, int W, int64_t* block_counts, int64_t* rows, int pass,
                       void* stream);
 
+/* ---- render_rays, the coarse + fine driver (SURVEY.md 8b "fused driver", 8c S2; upstream run_nerf.py, to which
+ * src/run_nerf_helpers.py:131-133 points): rays + stratified depths -> network on n_samples points -> raw2outputs ->
+ * sample_pdf(z_mid, weights[...,1:-1], n_importance, det = !perturb) -> sort(cat[z, z_samples]) -> network_fine on
+ * n_samples + n_importance points -> raw2outputs, as six launches on `stream`.  Inference form (no records, no
+ * density noise).  Every buffer is the caller's; R = n_rays, S = n_samples, Ni = n_importance.                    */
+typedef struct CtxNet {
+  const void* desc;      /* host blob of ctx_mlp_describe */
+  const void* wpacked;   /* device, ctx_mlp_pack */
+  const float* fparams;  /* device, ctx_mlp_pack */
+} CtxNet;
+typedef struct CtxRenderArgs {
+  int H, W;                          /* get_rays(H, W, K, c2w): K = [[fx,0,cx],[0,fy,cy],[0,0,1]] */
+  float fx, fy, cx, cy;
+  const float* c2w;                  /* device [3,4], leading dimension c2w_ld */
+  int c2w_ld;
+  const int64_t* ray_idx;            /* nullable: flat pixel ids y*W+x; NULL = pixels 0..n_rays-1 */
+  int64_t n_rays;
+  float near, far;
+  int lindisp, perturb;              /* perturb != 0: jittered depths and random u (Philox(seed [+ *seed_dev])) */
+  uint64_t seed;
+  const uint64_t* seed_dev;          /* nullable device counter added to seed */
+  const float* sphere;               /* HOST, nullable: (cx,cy,cz,r) -> per-ray near/far from the ray/sphere interval */
+  int n_samples, n_importance;       /* n_importance == 0: single pass, results in the final maps */
+  int white_bkgd;
+  int L_pts, L_dirs;                 /* encoding frequencies (10 / 4); L_dirs == 0 for a net without view directions */
+  int max_sms;                       /* SM budget of the MLP launches (0 = whole GPU) */
+  CtxNet coarse, fine;               /* fine.desc == NULL: the coarse network serves both passes */
+  /* workspace (device) */
+  float *rays_o, *rays_d, *viewdirs; /* [R,3] each; viewdirs nullable when L_dirs == 0 */
+  float *z_coarse, *raw_coarse, *weights_coarse;            /* [R,S], [R,S,4], [R,S] */
+  float *z_samples, *z_fine, *raw_fine, *weights_fine;      /* [R,Ni], [R,S+Ni], [R,S+Ni,4], [R,S+Ni] */
+  /* outputs (device): coarse maps (used when n_importance > 0) and final maps */
+  float *rgb0, *disp0, *acc0, *depth0;                      /* [R,3], [R], [R], [R] */
+  float *rgb_map, *disp_map, *acc_map, *depth_map;
+} CtxRenderArgs;
+int ctx_render_rays(const CtxRenderArgs* args, void* stream);
+int ctx_render_args_bytes(void);   /* sizeof(CtxRenderArgs) in the library (layout check for bindings) */
+
 /* ---- gradient all-reduce: the one exchange step of the ray-sharded training step, replacing the
  * reduce-add of nn.DataParallel (src/training/trainer.py:134-135).  NCCL is opened at run time (dlopen; `path`
  * nullable = "libnccl.so.2" by soname), so the library has no link-time dependency on it; every call below returns

@@ -47,6 +47,20 @@ def test_argument_errors_do_not_need_a_gpu(libpath):
                                 None, None) == -1
 
 
+def test_render_args_struct_layout_matches_the_library(libpath):
+    """The ctypes mirror of CtxRenderArgs has the size the library was compiled with, and the driver rejects an
+    empty argument block without touching the GPU."""
+    from ctxnerf import _lib
+    lib = _lib.lib()
+    assert lib.ctx_render_args_bytes() == ctypes.sizeof(_lib.CtxRenderArgs)
+    assert lib.ctx_render_rays(None, None) == -1
+    a = _lib.CtxRenderArgs()
+    a.n_rays, a.n_samples = 0, 64
+    assert lib.ctx_render_rays(ctypes.byref(a), None) == 0          # no rays: nothing to do
+    a.n_rays = 16
+    assert lib.ctx_render_rays(ctypes.byref(a), None) == -1         # no network / buffers
+
+
 def test_communicator_binding_loads_nccl_at_run_time(libpath):
     """ctx_comm_*: no link-time dependency on NCCL (the library must load without it), a clear error before
     ctx_comm_load, and -- with the NCCL copy torch ships -- the 2.x version check.  No GPU work."""

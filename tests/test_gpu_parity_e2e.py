@@ -10,6 +10,7 @@
 * ctx_adam_step against torch.optim.Adam, ctx_mse_fwd_bwd against img2mse + autograd.
 * N-rank all-reduced gradients == single-process sum, spawned here when >= 2 GPUs are visible.
 """
+import ctypes
 import os
 import subprocess
 import sys
@@ -261,6 +262,43 @@ def test_mse_kernel_matches_img2mse_autograd(cuda):
         call("ctx_mse_fwd_bwd", ptr(a.detach()), None, ptr(t), R * 3, 1.0, ptr(loss), ptr(ga), None, stream_ptr(cuda))
         torch.cuda.synchronize()
         assert abs(loss.item() - rh.img2mse(a, t).item()) <= 1e-6
+
+
+def test_render_rays_driver_equals_the_kernel_sequence(cuda):
+    """ctx_render_rays (csrc/render.cu, the C-ABI driver behind NerfTrainer.render) enqueues the same six launches a
+    host would issue one by one: every intermediate and every map must be bit-identical to that sequence -- for the
+    deterministic render and for the jittered one (same Philox seeds)."""
+    from ctxnerf import ops
+    from ctxnerf.train import NerfTrainer
+    from ctxnerf.workloads import orbit_camera
+    K, c2w = orbit_camera()
+    tr = NerfTrainer(800, 800, K, c2w, device=cuda, seed=3)
+    idx = torch.randint(0, 640000, (1500,), device=cuda)
+    S, Ni = tr.N_samples, tr.N_importance
+    for perturb, seed in ((False, 0), (True, 1234)):
+        got = tr._render(idx, perturb=perturb, seed=seed)
+        r = ops.raygen(tr.H, tr.W, tr.K, tr.c2w, ray_idx=idx, n_samples=S, near=tr.near, far=tr.far,
+                       lindisp=tr.lindisp, perturb=perturb, seed=seed, want_viewdirs=True)
+        o, d, v, z_c = r["rays_o"], r["rays_d"], r["viewdirs"], r["z_vals"]
+        R = o.shape[0]
+        raw_c = torch.empty(R * S, 4, device=cuda)
+        tr._fwd(tr.coarse, (o, d, v, z_c), R * S, raw_c, None)
+        comp_c = tr._composite(raw_c, z_c, d, R, S)
+        zs, z_f = ops.resample_merge(z_c, comp_c[3], Ni, det=not perturb, seed=seed + 1)
+        raw_f = torch.empty(R * (S + Ni), 4, device=cuda)
+        tr._fwd(tr.fine, (o, d, v, z_f), R * (S + Ni), raw_f, None)
+        comp_f = tr._composite(raw_f, z_f, d, R, S + Ni)
+        torch.cuda.synchronize()
+        assert torch.equal(got["z_f"], z_f) and torch.equal(got["raw_f"], raw_f)
+        for a, b in zip(got["comp_c"] + got["comp_f"], comp_c + comp_f):
+            assert torch.equal(a, b) or (torch.isnan(a) == torch.isnan(b)).all() and torch.equal(
+                torch.nan_to_num(a), torch.nan_to_num(b))
+    # argument errors come back as codes, not crashes
+    from ctxnerf import _lib
+    assert _lib.lib().ctx_render_rays(None, None) == -1
+    bad = _lib.CtxRenderArgs()
+    bad.n_rays, bad.n_samples = 4, 64
+    assert _lib.lib().ctx_render_rays(ctypes.byref(bad), None) == -1
 
 
 def test_allreduced_gradients_of_two_ranks_equal_single_process_sum(cuda):
