@@ -554,7 +554,7 @@ def test_composite_train_matches_separate_kernels(cuda):
         call("ctx_composite_train", ptr(rcu), ptr(zcu), ptr(dcu), None, R, S, 1, ptr(tcu), 1.0 / (3 * R), ptr(loss),
              ptr(g_raw), ptr(w), ptr(rgb), stream_ptr(cuda))
         torch.cuda.synchronize()
-        assert abs(loss.item() - l_sep.item()) <= 2e-6 * abs(l_sep.item())
+        assert abs(loss.item() - l_sep.item()) <= 1e-5 * abs(l_sep.item())      # fp32 sum of 3R terms in atomic order (north star: 1e-5)
         assert torch.equal(w, out[3].detach()) and torch.equal(rgb, out[0].detach())
         sc = rc.grad.abs().amax(dim=(1, 2), keepdim=True).clamp_min(1e-20)
         assert ((g_raw - rc.grad).abs() <= 1e-5 * sc).all()
