@@ -40,6 +40,7 @@ struct RaygenParams {
   float* viewdirs;  // optional [n,3]
   float* z_vals;    // optional [n, n_samples]
   float* near_far;  // optional [n,2]
+  int rays_per_iter;  // rays a warp builds per iteration (power of two, >= rows per pass, <= 32; set by the launcher)
 };
 
 // z(s) before jitter
@@ -64,7 +65,7 @@ __device__ __forceinline__ float stratified_depth(float near, float far, int S, 
 // `lane` / `nl`: position in and size of the lane group that shares this ray (8, 16 or 32 lanes).
 __device__ __forceinline__ void write_z_row(float* __restrict__ zrow, float near, float far, int S, int lindisp,
                                             int perturb, const float* __restrict__ jrow, uint64_t seed,
-                                            uint64_t ray, int lane, int nl = 32) {
+                                            uint64_t ray, int lane, int nl = 32, float step_in = -1.0f) {
   if ((S & 3) != 0 || S < 4) {   // ragged sample counts: element-wise path
     for (int s = lane; s < S; s += nl) {
       float u = 0.f;
@@ -73,8 +74,9 @@ __device__ __forceinline__ void write_z_row(float* __restrict__ zrow, float near
     }
     return;
   }
-  const float step = __fdiv_rn(1.0f, (float)(S - 1));
-  const float inear = 1.0f / near, ifar = 1.0f / far;
+  const float step = step_in >= 0.0f ? step_in : __fdiv_rn(1.0f, (float)(S - 1));   // (callers in a loop pass it in)
+  float inear = 0.f, ifar = 0.f;
+  if (lindisp) { inear = 1.0f / near; ifar = 1.0f / far; }
   const int half = S / 2;
   auto base = [&](int i) -> float {
     const float t = (i < half) ? fmaf(step, (float)i, 0.0f) : fmaf(-step, (float)(S - 1 - i), 1.0f);
@@ -132,12 +134,17 @@ __device__ __forceinline__ void ndc_warp(int H, int W, float focal, float near, 
 }
 
 __global__ void __launch_bounds__(kRayWarps * 32) raygen_kernel(RaygenParams p) {
-  // a group of `nl` lanes (8/16/32, chosen so that one pass of quads covers the S depths) shares a ray
+  // A warp takes 32 rays per iteration.  Phase 1: lane l builds ray r0 + l ONCE (pixel split, the two intrinsics
+  // divisions, rotation, norm, view direction, sphere interval) and stores its origin / direction / view direction.
+  // Phase 2: the depth rows, a group of `nl` lanes (8/16/32, chosen so that one pass of quads covers the S depths)
+  // per ray, near / far handed over by shuffle.  (Before: every lane of a group redid the whole per-ray setup --
+  // a third of the kernel's instructions in the ncu source page, and the kernel is issue-bound.)
   const int nl = p.n_samples > 64 ? 32 : (p.n_samples > 32 ? 16 : 8);
-  const int gpw = 32 / nl;                                   // rays per warp per iteration
-  const int lane = (threadIdx.x & 31) & (nl - 1);
-  const int64_t warp0 = ((int64_t)blockIdx.x * kRayWarps + (threadIdx.x >> 5)) * gpw + ((threadIdx.x & 31) / nl);
-  const int64_t nwarps = (int64_t)gridDim.x * kRayWarps * gpw;
+  const int gpw = 32 / nl;                                   // depth rows written per pass
+  const int l32 = threadIdx.x & 31;
+  const int lane = l32 & (nl - 1), sub = l32 / nl;
+  const int64_t warp0 = (int64_t)blockIdx.x * kRayWarps + (threadIdx.x >> 5);
+  const int64_t nwarps = (int64_t)gridDim.x * kRayWarps;
   // camera (uniform loads)
   float rot[3][3], org[3];
 #pragma unroll
@@ -147,46 +154,68 @@ __global__ void __launch_bounds__(kRayWarps * 32) raygen_kernel(RaygenParams p) 
     org[k] = __ldg(p.c2w + k * p.c2w_ld + 3);
   }
   const uint64_t seed = p.seed + (p.seed_dev ? *p.seed_dev : 0ull);
-  for (int64_t r = warp0; r < p.n_rays; r += nwarps) {
-    const int64_t pix = p.ray_idx ? p.ray_idx[r] : r;
-    const uint32_t pix32 = (uint32_t)pix;                       // H*W < 2^31 is checked by the launcher
-    const int py = (int)(pix32 / (uint32_t)p.W), px = (int)(pix32 - (uint32_t)py * (uint32_t)p.W);
-    const float a = ((float)px - p.cx) / p.fx;
-    const float b = -((float)py - p.cy) / p.fy;
-    const float c = -1.0f;
-    float dx = (a * rot[0][0] + b * rot[0][1]) + c * rot[0][2];
-    float dy = (a * rot[1][0] + b * rot[1][1]) + c * rot[1][2];
-    float dz = (a * rot[2][0] + b * rot[2][1]) + c * rot[2][2];
-    float ox = org[0], oy = org[1], oz = org[2];
-    // viewdirs are taken before the NDC warp (upstream render())
-    const float inv = sqrtf(dx * dx + dy * dy + dz * dz);
-    const float vx = dx / inv, vy = dy / inv, vz = dz / inv;
-    if (p.use_ndc) ndc_warp(p.H, p.W, p.ndc_focal, p.ndc_near, ox, oy, oz, dx, dy, dz);
+  const float zstep = p.n_samples > 1 ? __fdiv_rn(1.0f, (float)(p.n_samples - 1)) : 0.0f;
+  const int rpi = p.rays_per_iter;                           // 32 for large launches; fewer so that a small batch
+  for (int64_t r0 = warp0 * rpi; r0 < p.n_rays; r0 += nwarps * rpi) {   // (a 4096-ray training step) still covers the SMs
+    const int64_t r = r0 + l32;
     float near = p.near, far = p.far;
-    if (p.use_sphere) {
-      // |o + t d - c|^2 = r^2 ; rays that miss get near = far = |o - c| projected distance
-      const float lx = ox - p.sph_cx, ly = oy - p.sph_cy, lz = oz - p.sph_cz;
-      const float A = dx * dx + dy * dy + dz * dz;
-      const float Bq = lx * dx + ly * dy + lz * dz;
-      const float Cq = lx * lx + ly * ly + lz * lz - p.sph_r * p.sph_r;
-      const float disc = Bq * Bq - A * Cq;
-      if (disc > 0.f) {
-        const float sq = sqrtf(disc);
-        near = fmaxf((-Bq - sq) / A, 0.f);
-        far = fmaxf((-Bq + sq) / A, near);
-      } else {
-        near = far = fmaxf(-Bq / A, 0.f);
+    if (l32 < rpi && r < p.n_rays) {
+      const int64_t pix = p.ray_idx ? p.ray_idx[r] : r;
+      const uint32_t pix32 = (uint32_t)pix;                       // H*W < 2^31 is checked by the launcher
+      const int py = (int)(pix32 / (uint32_t)p.W), px = (int)(pix32 - (uint32_t)py * (uint32_t)p.W);
+      const float a = ((float)px - p.cx) / p.fx;
+      const float b = -((float)py - p.cy) / p.fy;
+      const float c = -1.0f;
+      float dx = (a * rot[0][0] + b * rot[0][1]) + c * rot[0][2];
+      float dy = (a * rot[1][0] + b * rot[1][1]) + c * rot[1][2];
+      float dz = (a * rot[2][0] + b * rot[2][1]) + c * rot[2][2];
+      float ox = org[0], oy = org[1], oz = org[2];
+      // viewdirs are taken before the NDC warp (upstream render())
+      const float inv = sqrtf(dx * dx + dy * dy + dz * dz);
+      const float vx = dx / inv, vy = dy / inv, vz = dz / inv;
+      if (p.use_ndc) ndc_warp(p.H, p.W, p.ndc_focal, p.ndc_near, ox, oy, oz, dx, dy, dz);
+      if (p.use_sphere) {
+        // |o + t d - c|^2 = r^2 ; rays that miss get near = far = |o - c| projected distance
+        const float lx = ox - p.sph_cx, ly = oy - p.sph_cy, lz = oz - p.sph_cz;
+        const float A = dx * dx + dy * dy + dz * dz;
+        const float Bq = lx * dx + ly * dy + lz * dz;
+        const float Cq = lx * lx + ly * ly + lz * lz - p.sph_r * p.sph_r;
+        const float disc = Bq * Bq - A * Cq;
+        if (disc > 0.f) {
+          const float sq = sqrtf(disc);
+          near = fmaxf((-Bq - sq) / A, 0.f);
+          far = fmaxf((-Bq + sq) / A, near);
+        } else {
+          near = far = fmaxf(-Bq / A, 0.f);
+        }
+      }
+      // three consecutive floats per lane: the warp's 32 rays fill one contiguous 384-byte span per array
+      float* po = p.rays_o + r * 3;
+      po[0] = ox; po[1] = oy; po[2] = oz;
+      float* pd = p.rays_d + r * 3;
+      pd[0] = dx; pd[1] = dy; pd[2] = dz;
+      if (p.viewdirs) {
+        float* pv = p.viewdirs + r * 3;
+        pv[0] = vx; pv[1] = vy; pv[2] = vz;
+      }
+      if (p.near_far) { p.near_far[r * 2] = near; p.near_far[r * 2 + 1] = far; }
+    }
+    if (p.z_vals) {
+      const int64_t left = p.n_rays - r0;
+      const int cnt = left < rpi ? (int)left : rpi;             // warp-uniform
+      for (int j = 0; j < cnt; j += gpw) {
+        const int owner = j + sub;                               // lane that built this group's ray (< 32)
+        float nr = p.near, fr = p.far;
+        if (p.use_sphere) {
+          nr = __shfl_sync(CTX_FULL_MASK, near, owner);
+          fr = __shfl_sync(CTX_FULL_MASK, far, owner);
+        }
+        const int64_t rr = r0 + owner;
+        if (rr < p.n_rays)
+          write_z_row(p.z_vals + rr * p.n_samples, nr, fr, p.n_samples, p.lindisp, p.perturb,
+                      p.jitter ? p.jitter + rr * p.n_samples : nullptr, seed, (uint64_t)rr, lane, nl, zstep);
       }
     }
-    if (lane < 3) {
-      p.rays_o[r * 3 + lane] = lane == 0 ? ox : lane == 1 ? oy : oz;
-      p.rays_d[r * 3 + lane] = lane == 0 ? dx : lane == 1 ? dy : dz;
-      if (p.viewdirs) p.viewdirs[r * 3 + lane] = lane == 0 ? vx : lane == 1 ? vy : vz;
-    }
-    if (p.near_far && lane < 2) p.near_far[r * 2 + lane] = lane == 0 ? near : far;
-    if (p.z_vals)
-      write_z_row(p.z_vals + r * p.n_samples, near, far, p.n_samples, p.lindisp, p.perturb,
-                  p.jitter ? p.jitter + r * p.n_samples : nullptr, seed, (uint64_t)r, lane, nl);
   }
 }
 
@@ -285,7 +314,13 @@ extern "C" int ctx_raygen_fwd(int H, int W, float fx, float fy, float cx, float 
   p.sph_cz = use_sphere ? sphere[2] : 0.f; p.sph_r = use_sphere ? sphere[3] : 0.f;
   p.rays_o = rays_o; p.rays_d = rays_d; p.viewdirs = viewdirs;
   p.z_vals = n_samples > 0 ? z_vals : nullptr; p.near_far = near_far;
-  ctx::raygen_kernel<<<ctx::warp_grid(n_rays, ctx::kRayWarps), ctx::kRayWarps * 32, 0,
+  {
+    const int nl = n_samples > 64 ? 32 : (n_samples > 32 ? 16 : 8);
+    int rpi = 32;                                       // halve while the launch would leave SMs without a warp
+    while (rpi > 32 / nl && n_rays < (int64_t)rpi * ctx::kRayWarps * ctx::num_sms() * 2) rpi >>= 1;
+    p.rays_per_iter = rpi;
+  }
+  ctx::raygen_kernel<<<ctx::warp_grid(ctx::ceil_div(n_rays, p.rays_per_iter), ctx::kRayWarps), ctx::kRayWarps * 32, 0,
                        (cudaStream_t)stream>>>(p);
   CTX_RETURN_LAST();
 }
