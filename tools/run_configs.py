@@ -66,7 +66,23 @@ for lr in (12, 14, 16, 18, 20, 22):
         t = timeit(lambda: call("ctx_composite_train", ptr(raw), ptr(z), ptr(d), None, R, S, 1, ptr(tgt), 1.0 / (3 * R),
                                 ptr(loss), ptr(g_raw), ptr(wts), None, stream_ptr(dev)), iters=3, warm=1)
         row["composite_train_gbs"] = R * (40 * S + 24) / t / 1e9
-        del tgt, g_raw, wts
+        # separate backward (all five output gradients given): reads raw 16S + z 4S + g_weights 4S + 36, writes g_raw 16S
+        g = [torch.randn(R, 3, device=dev), torch.randn(R, device=dev), torch.randn(R, device=dev),
+             torch.randn(R, S, device=dev), torch.randn(R, device=dev)]
+        t = timeit(lambda: call("ctx_composite_bwd", ptr(raw), ptr(z), ptr(d), None, R, S, 1, ptr(g[0]), ptr(g[1]),
+                                ptr(g[2]), ptr(g[3]), ptr(g[4]), ptr(g_raw), stream_ptr(dev)), iters=3, warm=1)
+        row["composite_bwd_gbs"] = R * (40 * S + 36) / t / 1e9
+        del tgt, g_raw, wts, g
+        # get_rays + view directions + stratified depths of a sqrt(R) x sqrt(R) image: 36 + 4S B written per ray
+        side = 1 << (lr // 2)
+        Kc = [[1111.1, 0, side / 2.0], [0, 1111.1, side / 2.0], [0, 0, 1]]
+        c2w_i = torch.eye(4, device=dev)[:3].contiguous()
+        ro = (torch.empty(R, 3, device=dev), torch.empty(R, 3, device=dev), torch.empty(R, 3, device=dev), torch.empty(R, S, device=dev))
+        for tag, pert in (("raygen_gbs", False), ("raygen_jitter_gbs", True)):
+            t = timeit(lambda: ops.raygen(side, side, Kc, c2w_i, n_samples=S, near=2., far=6., perturb=pert, seed=1,
+                                          want_viewdirs=True, out=ro), iters=3, warm=1)
+            row[tag] = R * (36 + 4 * S) / t / 1e9
+        del ro
         N = 2 * S
         if N <= 1024:
             bins_c, w_c = z[:, :S - 1].contiguous(), w[:, :S - 2].contiguous()   # (not part of the timed call)
