@@ -100,11 +100,13 @@ class NerfTrainer:
         if self.world_size > 1 and os.environ.get("CTXNERF_NCCL", "1") != "0" and dist_backend() == "nccl":
             self.comm = BucketComm(dev)
         self.reduce_gradients = True       # (tools/dist_check.py turns the exchange off for its single-process sums)
-        # with the library's binding the bucket goes in two halves: the fine network's right behind its wgrad, beside
-        # the coarse chain still running on the side stream, the coarse network's after the join (CTXNERF_SPLIT_REDUCE=0:
-        # one all-reduce of the whole bucket after the join)
+        # CTXNERF_SPLIT_REDUCE=1: the bucket goes in two halves -- the fine network's right behind its wgrad, beside the
+        # coarse chain still running on the side stream, the coarse network's after the join.  Measured on 8 GPUs it is
+        # SLOWER than one whole-bucket call after the join (4.45 vs 4.39 ms: the early NCCL kernel waits for the slowest
+        # rank while holding SMs the coarse chain wants), so the default is the single call
+        # (profiles/r02/allreduce_routes_8gpu.txt)
         self._n_coarse = sum(p.numel() for p in self.coarse.parameters())
-        self.split_reduce = self.comm is not None and os.environ.get("CTXNERF_SPLIT_REDUCE", "1") != "0"
+        self.split_reduce = self.comm is not None and os.environ.get("CTXNERF_SPLIT_REDUCE", "0") == "1"
         self._loss = torch.zeros(1, device=dev)
         # device-side step state: [0] Philox seed offset, [1] Adam step count (ctx_step_tick advances both)
         self._ctr = torch.zeros(2, device=dev, dtype=torch.int64)
