@@ -452,14 +452,37 @@ class NerfTrainer:
         per-ray near/far from the bounding sphere of the normalised mesh, `n_samples` depths per ray, no hierarchical
         pass).  Maps are [H,W,...] for a whole view, [n,...] for a pixel list."""
         dev = self.device
-        with torch.cuda.device(dev):
-            r = ops.raygen(H, W, K, torch.as_tensor(c2w, dtype=torch.float32).to(dev), n_samples=n_samples,
-                           near=self.near if near is None else near, far=self.far if far is None else far,
-                           sphere=sphere, want_viewdirs=True, ray_idx=ray_idx)
-            n = r["rays_o"].shape[0]
-            raw = torch.empty(n * n_samples, 4, device=dev)
-            self._fwd(self.fine, (r["rays_o"], r["rays_d"], r["viewdirs"], r["z_vals"]), n * n_samples, raw, None)
-            rgb, disp, acc, _, depth = self._composite(raw, r["z_vals"], r["rays_d"], n, n_samples)
+        f32 = dict(device=dev, dtype=torch.float32)
+        c2w_d = torch.as_tensor(c2w, dtype=torch.float32).to(dev).contiguous()
+        if ray_idx is not None:
+            ray_idx = ray_idx.to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
+        n = H * W if ray_idx is None else ray_idx.numel()
+        o, d, v = (torch.empty(n, 3, **f32) for _ in range(3))
+        z, raw, w = torch.empty(n, n_samples, **f32), torch.empty(n * n_samples, 4, **f32), torch.empty(n, n_samples, **f32)
+        rgb, disp, acc, depth = torch.empty(n, 3, **f32), torch.empty(n, **f32), torch.empty(n, **f32), torch.empty(n, **f32)
+        if n > 0:
+            # the single-pass form of ctx_render_rays (n_importance = 0) with the fine network and the sphere interval
+            a = _lib.CtxRenderArgs()
+            a.H, a.W = int(H), int(W)
+            a.fx, a.fy, a.cx, a.cy = float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2])
+            a.c2w, a.c2w_ld = c2w_d.data_ptr(), c2w_d.stride(0)
+            a.ray_idx, a.n_rays = (None if ray_idx is None else ray_idx.data_ptr()), n
+            a.near, a.far = float(self.near if near is None else near), float(self.far if far is None else far)
+            a.lindisp, a.perturb, a.seed, a.seed_dev = 0, 0, 0, None
+            sph = None
+            if sphere is not None:
+                sph = (ctypes.c_float * 4)(*[float(x) for x in sphere])
+                a.sphere = ctypes.addressof(sph)
+            a.n_samples, a.n_importance, a.white_bkgd = int(n_samples), 0, int(self.white_bkgd)
+            a.L_pts, a.L_dirs, a.max_sms = self.fine.L_pts, self.fine.L_dirs, 0
+            wp, _, fp = self._pk[self.fine]
+            a.coarse.desc, a.coarse.wpacked, a.coarse.fparams = ctypes.addressof(self.fine._desc.blob), wp.data_ptr(), fp.data_ptr()
+            for name, t in (("rays_o", o), ("rays_d", d), ("viewdirs", v), ("z_coarse", z), ("raw_coarse", raw),
+                            ("weights_coarse", w), ("rgb_map", rgb), ("disp_map", disp), ("acc_map", acc),
+                            ("depth_map", depth)):
+                setattr(a, name, t.data_ptr())
+            with torch.cuda.device(dev):
+                call("ctx_render_rays", ctypes.byref(a), stream_ptr(dev))
         if ray_idx is None:
             return dict(rgb_map=rgb.reshape(H, W, 3), disp_map=disp.reshape(H, W), acc_map=acc.reshape(H, W),
                         depth_map=depth.reshape(H, W))

@@ -293,6 +293,20 @@ def test_render_rays_driver_equals_the_kernel_sequence(cuda):
         for a, b in zip(got["comp_c"] + got["comp_f"], comp_c + comp_f):
             assert torch.equal(a, b) or (torch.isnan(a) == torch.isnan(b)).all() and torch.equal(
                 torch.nan_to_num(a), torch.nan_to_num(b))
+    # single-pass form (n_importance = 0) with the bounding-sphere interval: NerfTrainer.render_view (BASELINE config 4)
+    from ctxnerf.workloads import multiview_cameras
+    cams, sph = multiview_cameras()
+    Kv, cv = cams[1]
+    idx4 = torch.randint(0, 1024 * 1024, (3000,), device=cuda)
+    got = tr.render_view(1024, 1024, Kv, cv, n_samples=192, sphere=sph, ray_idx=idx4)
+    r = ops.raygen(1024, 1024, Kv, torch.as_tensor(cv, dtype=torch.float32).to(cuda), n_samples=192, near=tr.near,
+                   far=tr.far, sphere=sph, want_viewdirs=True, ray_idx=idx4)
+    raw = torch.empty(3000 * 192, 4, device=cuda)
+    tr._fwd(tr.fine, (r["rays_o"], r["rays_d"], r["viewdirs"], r["z_vals"]), 3000 * 192, raw, None)
+    rgb, disp, acc, _, depth = tr._composite(raw, r["z_vals"], r["rays_d"], 3000, 192)
+    torch.cuda.synchronize()
+    assert torch.equal(got["rgb_map"], rgb) and torch.equal(got["acc_map"], acc) and torch.equal(got["depth_map"], depth)
+    assert torch.equal(torch.nan_to_num(got["disp_map"]), torch.nan_to_num(disp))
     # argument errors come back as codes, not crashes
     from ctxnerf import _lib
     assert _lib.lib().ctx_render_rays(None, None) == -1
