@@ -1,27 +1,31 @@
-"""Summarise an `ncu --page source --csv` export (tools/source_profile.sh): executed warp instructions and stall
-samples per CUDA source line, heaviest first.  usage: python tools/source_report.py <csv> [top_n]"""
+"""Summarise an `ncu --page source --csv` export (tools/source_profile.sh): executed warp instructions and stall samples per
+CUDA source line, heaviest first (the export holds a CUDA view and a SASS view: percentages are of the CUDA view only).
+usage: python tools/source_report.py <csv> [top_n] [--by-samples]"""
 import csv, sys, collections
-path = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+path = args[0]; top = int(args[1]) if len(args) > 1 else 40
+by_samples = "--by-samples" in sys.argv
 rows = list(csv.reader(open(path)))
-# the export holds one table per source file: a 'File Path' row, a 'Function Name' row, a header, then lines
-per_line = collections.OrderedDict(); hdr = None; fpath = None; total = 0; samples = 0
+agg = {}; hdr = None; fpath = None
 for r in rows:
     if not r: continue
     if r[0] == "File Path": fpath = r[1].split("/")[-1]; hdr = None; continue
     if r[0] == "Function Name": continue
-    if r[0] == "Line No" or r[0] == "#":
-        hdr = r; continue
-    if hdr is None or fpath is None: continue
+    if r[0] in ("Line No", "#"): hdr = r; continue
+    if hdr is None or fpath is None or not r[0].strip().isdigit(): continue        # SASS-view rows carry no line number
     try:
-        i_inst = hdr.index("Instructions Executed"); i_smp = hdr.index("# Samples")
-        ln = r[0]; src = r[1]
-        inst = int(float(r[i_inst] or 0)); smp = int(float(r[i_smp] or 0))
+        inst = int(float(r[hdr.index("Instructions Executed")] or 0)); smp = int(float(r[hdr.index("# Samples")] or 0))
     except (ValueError, IndexError):
         continue
-    key = (fpath, ln)
-    if key not in per_line: per_line[key] = [src.strip(), 0, 0]
-    per_line[key][1] += inst; per_line[key][2] += smp
-    total += inst; samples += smp
-print(f"total warp instructions {total:,}   stall samples {samples:,}")
-for (f, ln), (src, inst, smp) in sorted(per_line.items(), key=lambda kv: -kv[1][1])[:top]:
-    print(f"{100.0 * inst / max(total, 1):5.1f}% inst {100.0 * smp / max(samples, 1):5.1f}% smp  {f}:{ln:>4}  {src[:110]}")
+    a = agg.setdefault((fpath, r[0]), [r[1].strip(), 0, 0, collections.Counter()])
+    a[1] += inst; a[2] += smp
+    for k in hdr:
+        if k.startswith("stall_") and "(" not in k:
+            try: a[3][k[6:]] += int(float(r[hdr.index(k)] or 0))
+            except ValueError: pass
+t_inst = sum(a[1] for a in agg.values()) or 1; t_smp = sum(a[2] for a in agg.values()) or 1
+print(f"warp instructions attributed to source lines {t_inst:,}   stall samples {t_smp:,}")
+order = sorted(agg.items(), key=lambda kv: -(kv[1][2] if by_samples else kv[1][1]))[:top]
+for (f, ln), (src, inst, smp, st) in order:
+    why = ", ".join(f"{k} {v}" for k, v in st.most_common(3) if v)
+    print(f"{100.0 * inst / t_inst:5.1f}% inst {100.0 * smp / t_smp:5.1f}% smp  {f}:{ln:>4}  {src[:84]}   [{why}]")
