@@ -78,8 +78,12 @@ __device__ __forceinline__ void write_z_row(float* __restrict__ zrow, float near
   float inear = 0.f, ifar = 0.f;
   if (lindisp) { inear = 1.0f / near; ifar = 1.0f / far; }
   const int half = S / 2;
-  auto base = [&](int i) -> float {
-    const float t = (i < half) ? fmaf(step, (float)i, 0.0f) : fmaf(-step, (float)(S - 1 - i), 1.0f);
+  const float fS1 = (float)(S - 1), fhalf = (float)half;
+  // base depth of sample index `fi` (an integer held in fp32: one int->float conversion per quad instead of one or two
+  // per depth -- the conversions run on the quarter-rate pipe and this kernel is issue-bound); same values as
+  // linspace_at: lower half step*i, upper half 1 - step*(S-1-i), one rounding each
+  auto base = [&](float fi) -> float {
+    const float t = (fi < fhalf) ? fmaf(step, fi, 0.0f) : fmaf(-step, fS1 - fi, 1.0f);
     if (lindisp) return 1.0f / (inear * (1.0f - t) + ifar * t);
     return near * (1.0f - t) + far * t;
   };
@@ -87,14 +91,13 @@ __device__ __forceinline__ void write_z_row(float* __restrict__ zrow, float near
     const int s0 = q << 2;
     float4 out;
     if (!perturb) {
-      out = make_float4(base(s0), base(s0 + 1), base(s0 + 2), base(s0 + 3));
+      const float f0 = (float)s0;
+      out = make_float4(base(f0), base(f0 + 1.0f), base(f0 + 2.0f), base(f0 + 3.0f));
     } else {
       float zb[6];
+      const float fm1 = (float)(s0 - 1);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        const int si = min(max(s0 - 1 + i, 0), S - 1);
-        zb[i] = base(si);
-      }
+      for (int i = 0; i < 6; ++i) zb[i] = base(fminf(fmaxf(fm1 + (float)i, 0.0f), fS1));   // neighbours, clamped to the row
       float u[4];
       if (jrow) {
         const float4 j4 = *reinterpret_cast<const float4*>(jrow + s0);
