@@ -196,7 +196,7 @@ composite_fwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z
 // composite_fwd + mse + composite_bwd.  It writes g_raw, optionally weights (the coarse pass feeds sample_pdf) and
 // rgb_map, and adds sum((rgb-target)^2) * loss_scale into loss[0] (one atomic per warp pass).
 template <int K, int G, bool TRAIN>
-__global__ void __launch_bounds__(kCompWarps * 32, K <= 4 ? 3 : (K <= 8 ? 2 : 1))
+__global__ void __launch_bounds__(kCompWarps * 32, K <= 4 ? 4 : (K <= 8 ? 2 : 1))
 composite_bwd_kernel(const float4* __restrict__ raw, const float* __restrict__ z,
                      const float* __restrict__ rays_d, const float* __restrict__ noise,
                      int64_t R, int S_all, int vec, int white_bkgd,
