@@ -82,11 +82,21 @@ class BucketComm:
         if world_size < 2:
             raise RuntimeError("BucketComm needs an initialised torch.distributed group with more than one rank")
         path = os.environ.get("CTXNERF_NCCL_LIB") or _loaded_nccl_path()
-        _lib.call("ctx_comm_load", path.encode() if path else None)
+        on_gpu = dist.get_backend(group) == "nccl"
         token = torch.zeros(128, dtype=torch.uint8)
-        if rank == 0:
-            _lib.call("ctx_comm_unique_id", ctypes.c_void_p(token.data_ptr()))
-        carrier = token.to(device) if dist.get_backend(group) == "nccl" else token
+        local_error = None
+        try:                                   # local part: resolve NCCL, make the token
+            _lib.call("ctx_comm_load", path.encode() if path else None)
+            if rank == 0:
+                _lib.call("ctx_comm_unique_id", ctypes.c_void_p(token.data_ptr()))
+        except Exception as e:
+            local_error = e
+        # every rank learns whether every rank got this far BEFORE anyone enters the broadcast / the NCCL rendezvous
+        ok = torch.tensor([0 if local_error else 1], dtype=torch.int32, device=device if on_gpu else "cpu")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 0:
+            raise _lib.CtxNerfError(f"BucketComm: NCCL binding unavailable on at least one rank ({local_error})")
+        carrier = token.to(device) if on_gpu else token
         dist.broadcast(carrier, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         token = carrier.cpu().contiguous()
         handle = ctypes.c_void_p()

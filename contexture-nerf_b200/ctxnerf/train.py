@@ -98,7 +98,7 @@ class NerfTrainer:
         # step is then one graph); CTXNERF_NCCL=0 or a non-NCCL process group -> torch.distributed between two graphs
         self.comm = None
         if self.world_size > 1 and os.environ.get("CTXNERF_NCCL", "1") != "0" and dist_backend() == "nccl":
-            self.comm = BucketComm(dev)
+            self.comm = self._make_comm(dev)
         self.reduce_gradients = True       # (tools/dist_check.py turns the exchange off for its single-process sums)
         # CTXNERF_SPLIT_REDUCE=1: the bucket goes in two halves -- the fine network's right behind its wgrad, beside the
         # coarse chain still running on the side stream, the coarse network's after the join.  Measured on 8 GPUs it is
@@ -144,6 +144,28 @@ class NerfTrainer:
         self._ev0, self._ev1, self._ev2, self._ev3 = (torch.cuda.Event() for _ in range(4))
         with torch.cuda.device(dev):
             self._repack()
+
+    @staticmethod
+    def _make_comm(dev):
+        """The library's NCCL communicator, or None (-> torch.distributed's all-reduce) when it cannot be had on EVERY
+        rank: the outcome is agreed through the existing process group so that no rank waits in a collective the
+        others never enter.  A failure is reported, not hidden (stderr, once per rank)."""
+        import sys
+        import torch.distributed as dist
+        comm, err = None, None
+        try:
+            comm = BucketComm(dev)
+        except Exception as e:          # no NCCL shared object, version outside 2.x, init error
+            err = e
+        ok = torch.tensor([1 if comm is not None else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 1:
+            return comm
+        if comm is not None:
+            comm.close()
+        print(f"ctxnerf: ctx_allreduce unavailable on at least one rank ({err}); using torch.distributed for the "
+              "gradient all-reduce", file=sys.stderr, flush=True)
+        return None
 
     @property
     def step_count(self) -> int:
