@@ -187,3 +187,49 @@ def test_product_fails_loudly_without_cuda():
         texture_mapping(torch.zeros(1, 4, 2), torch.zeros(1, 3, 8, 8), "lanczos")
     with pytest.raises((_lib.CtxNerfError, RuntimeError)):
         rh.NeRF2D(D=8, W=256, input_ch=42, output_ch=3, skips=[4])(torch.zeros(4, 42))
+
+
+def _comm_worker(rank, world, port, q):
+    for p in (ROOT, PKG):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    # only rank 1 cannot find NCCL: the agreement step must make BOTH ranks give up before any rendezvous
+    if rank == 1:
+        os.environ["CTXNERF_NCCL_LIB"] = "/nonexistent/libnccl.so.2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from ctxnerf._lib import CtxNerfError
+        from ctxnerf.dist import BucketComm, dist_backend
+        assert dist_backend() == "gloo"
+        try:
+            BucketComm(torch.device("cpu"))
+            q.put((rank, "no error"))
+        except CtxNerfError as e:
+            assert "unavailable on at least one rank" in str(e)
+            # the process group is still usable afterwards (nobody is stuck in a half-entered collective)
+            t = torch.tensor([rank + 1])
+            dist.all_reduce(t)
+            q.put((rank, "agreed" if int(t) == 3 else "bad sum"))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_communicator_availability_is_agreed_across_ranks_gloo():
+    """BucketComm (the library's NCCL binding) when ONE rank cannot load NCCL: every rank raises the same error after
+    the agreement all-reduce, none enters the token broadcast / the NCCL rendezvous alone, and the process group stays
+    usable -- which is what lets NerfTrainer fall back to torch.distributed on all ranks together."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_comm_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, "agreed"), (1, "agreed")], res
