@@ -30,7 +30,8 @@ struct SampleTerms {
 // use -- with three sigmoids per sample that was a quarter of the kernels' instructions, and they are issue-bound.
 // y is clamped to <= 1e30 so that the Newton step never sees inf * 0 (sigmoid(x) for x < -69 is then 1e-30, not e^x).
 __device__ __forceinline__ float sigmoidf_(float x) {
-  const float y = 1.0f + fminf(__expf(-x), 1e30f);     // ex2.approx: |d sigmoid| <= s (1 - s) (2.4e-7 + 6e-8 |x|) < 1 ulp of 0.5
+  const float e = __expf(-x);                          // ex2.approx: |d sigmoid| <= s (1 - s) (2.4e-7 + 6e-8 |x|) < 1 ulp of 0.5
+  const float y = 1.0f + ((e > 1e30f) ? 1e30f : e);    // (a comparison, not fminf: a NaN logit must stay NaN)
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
   return fmaf(r, fmaf(-y, r, 1.0f), r);
@@ -38,7 +39,8 @@ __device__ __forceinline__ float sigmoidf_(float x) {
 
 __device__ __forceinline__ SampleTerms sample_terms(float sigma, float dist) {
   SampleTerms t;
-  t.expo = expf(-fmaxf(sigma, 0.0f) * dist);
+  const float dens = (sigma < 0.0f) ? 0.0f : sigma;     // relu that keeps a NaN density a NaN (fmaxf would return 0)
+  t.expo = expf(-dens * dist);
   t.alpha = 1.0f - t.expo;
   t.trans_factor = (1.0f - t.alpha) + 1e-10f;
   return t;

@@ -167,6 +167,28 @@ def test_composite_forward(cuda, R, S):
                 close_w(a, b, f"{n} R={R} S={S} white={white}")
 
 
+def test_composite_propagates_nan_logits(cuda):
+    """A diverged network must stay visible: a NaN colour logit or density gives NaN maps for THAT ray (as in the
+    oracle) and leaves the other rays untouched -- forward, backward and the fused training form."""
+    from ctxnerf import ops
+    raw, z, d = orc.cfg1_inputs(64, 64, seed=3)
+    clean = ops.composite(raw.to(cuda), z.to(cuda), d.to(cuda), None, True)
+    raw[5, 10, 1] = float("nan")
+    raw[9, 3, 3] = float("nan")
+    ref = orc.raw2outputs(raw, z, d, white_bkgd=True)
+    rc = raw.to(cuda).requires_grad_(True)
+    got = ops.composite(rc, z.to(cuda), d.to(cuda), None, True)
+    for g, r, c in zip(got, ref, clean):
+        g = g.detach().cpu()
+        assert torch.equal(torch.isnan(g), torch.isnan(r))
+        keep = torch.ones(64, dtype=torch.bool)
+        keep[[5, 9]] = False
+        assert torch.equal(g[keep], c.cpu()[keep])
+    assert bool(torch.isnan(got[0][5]).any()) and bool(torch.isnan(got[2][9]))
+    got[0].nan_to_num().sum().backward()
+    assert bool(torch.isfinite(rc.grad[0]).all())
+
+
 def test_composite_known_answers(cuda):
     from ctxnerf import run_nerf_helpers as rh
     raw = -torch.rand(4, 8, 4) - 0.1
