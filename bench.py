@@ -328,7 +328,8 @@ def main():
     tr = NerfTrainer(800, 800, K, c2w, near=2.0, far=6.0, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE,
                      perturb=1.0, white_bkgd=True, device=dev, seed=0)
     # per-rank synthetic batches (seed 0 + rank), resident on the device and mirrored in pinned host memory
-    g = torch.Generator().manual_seed(0 + rank)
+    from ctxnerf.dist import rank_generator
+    g = rank_generator(0, rank)              # the seed + rank stream of this rank's ray selection
     NB = 8
     idx_h = [torch.randint(0, 800 * 800, (RAYS_PER_GPU,), generator=g).pin_memory() for _ in range(NB)]
     tgt_h = [torch.rand(RAYS_PER_GPU, 3, generator=g).pin_memory() for _ in range(NB)]
