@@ -82,7 +82,7 @@ class BucketComm:
         if world_size < 2:
             raise RuntimeError("BucketComm needs an initialised torch.distributed group with more than one rank")
         path = os.environ.get("CTXNERF_NCCL_LIB") or _loaded_nccl_path()
-        on_gpu = dist.get_backend(group) == "nccl"
+        on_gpu = "nccl" in str(dist.get_backend(group))      # ("nccl", or the combined "cpu:gloo,cuda:nccl" default)
         token = torch.zeros(128, dtype=torch.uint8)
         local_error = None
         try:                                   # local part: resolve NCCL, make the token

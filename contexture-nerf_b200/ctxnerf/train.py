@@ -97,7 +97,7 @@ class NerfTrainer:
         # gradient all-reduce through the library's own NCCL binding (ctx_allreduce on the step's stream: the whole
         # step is then one graph); CTXNERF_NCCL=0 or a non-NCCL process group -> torch.distributed between two graphs
         self.comm = None
-        if self.world_size > 1 and os.environ.get("CTXNERF_NCCL", "1") != "0" and dist_backend() == "nccl":
+        if self.world_size > 1 and os.environ.get("CTXNERF_NCCL", "1") != "0" and "nccl" in dist_backend():
             self.comm = self._make_comm(dev)
         self.reduce_gradients = True       # (tools/dist_check.py turns the exchange off for its single-process sums)
         # CTXNERF_SPLIT_REDUCE=1: the bucket goes in two halves -- the fine network's right behind its wgrad, beside the
